@@ -1,0 +1,130 @@
+/*
+ * kdeb200.h -- C-ABI of libkdeb200.so: the B200 (sm_100a) implementation of the data-parallel
+ * hot path of KernelDensityEstimate.jl (multiscale Gibbs KDE-product sampler, brute-force
+ * Gaussian-kernel evaluation, leave-one-out likelihood).
+ *
+ * This is the drop-in boundary: the reference is pure Julia with no FFI of its own, so each
+ * entry point below names the reference function it replaces (paths relative to the reference
+ * repo) -- that is the call a maintainer re-points with `ccall` (INTEGRATION.md shows the
+ * Julia binding; kerneldensityestimate.jl_b200/_lib.py is the ctypes mirror used by the tests).
+ *
+ * Conventions
+ *   - every function returns 0 on success, nonzero on error; kdeb200_last_error() returns the
+ *     message for the calling thread (the reference raises ErrorException via error(...):
+ *     src/DualTree01.jl:311,382,414, src/MSGibbs01.jl:721 -- the binding turns nonzero into that).
+ *   - matrices are column-major exactly as Julia passes them (d x N => point i at [i*d, i*d+d)).
+ *   - indices inside tree arrays are the reference's 1-based node ids (NO_CHILD = -1).
+ *   - host buffers are owned by the caller and never retained; `_device` variants take device
+ *     pointers plus a cudaStream_t (as void*) and do not synchronise.
+ *   - Euclidean (+,-) manifolds only, d <= KDEB200_MAX_DIM, uniform bandwidth (multibandwidth
+ *     == 0, the only case the reference's typed constructors produce).  Anything else is an
+ *     error: there is no CPU fallback.
+ */
+#ifndef KDEB200_H
+#define KDEB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDEB200_MAX_DIM 8
+#define KDEB200_MAX_DENS 16
+
+#define KDEB200_F64 0 /* FP64 arithmetic (parity mode: 1e-12 eval, exact labels) */
+#define KDEB200_F32 1 /* FP32 arithmetic with MUFU ex2 (evaluation only, 1e-5) */
+
+typedef struct kdeb200_tree_s *kdeb200_tree_t; /* opaque device-resident BallTreeDensity */
+
+/* ---- library / device ----------------------------------------------------------------- */
+const char *kdeb200_last_error(void);
+int kdeb200_version(void);
+int kdeb200_device_count(int *count);
+/* Binds the calling process to CUDA device `device` (one process per GPU). */
+int kdeb200_init(int device);
+int kdeb200_shutdown(void);
+int kdeb200_device_props(int *sm_count, int *cc_major, int *cc_minor, int *clock_khz, size_t *free_bytes);
+
+/* ---- S0: tree handle --------------------------------------------------------------------
+ * Replaces nothing in the reference by itself: it is the hand-over of a host-built
+ * BallTreeDensity (src/BallTree01.jl:10-28, src/BallTreeDensity01.jl:11-24).  The arrays are the
+ * struct fields verbatim: means / bandwidth are 2N*d, weights / left / right / perm are 2N.
+ * The library flattens them into level-ordered device records (DESIGN.md "HBM layout"). */
+int kdeb200_tree_create(int d, int64_t N, const double *means, const double *bandwidth, const double *weights,
+                        const int64_t *left_child, const int64_t *right_child, const int64_t *permutation,
+                        kdeb200_tree_t *out);
+int kdeb200_tree_destroy(kdeb200_tree_t t);
+int kdeb200_tree_info(kdeb200_tree_t t, int *d, int64_t *N, int *nlevels, int64_t *device_bytes);
+
+/* Host-side construction of the reference's tree arrays (makeBallTreeDensity,
+ * src/BallTreeDensity01.jl:192-231 -> buildTree! src/BallTree01.jl:415-434).  For hosts without
+ * Julia (the python mirror) and as the fast path for SURVEY.md 8f.1; a Julia caller keeps using
+ * its own builder and passes the arrays to kdeb200_tree_create.  All outputs are caller-allocated:
+ * centers, ranges, means, bandwidth: 2N*d; weights_out, left, right, lowest, highest, perm: 2N. */
+int kdeb200_tree_build_host(int d, int64_t N, const double *points, const double *weights, const double *bw_var,
+                            double *centers, double *ranges, double *weights_out, double *means,
+                            double *bandwidth, int64_t *left_child, int64_t *right_child,
+                            int64_t *lowest_leaf, int64_t *highest_leaf, int64_t *permutation);
+
+/* ---- S1: multiscale Gibbs product sampler -------------------------------------------------
+ * Replaces gibbs1(Ndens, trees, Np, Niter, pts, ind, randU, randN; ...) src/MSGibbs01.jl:527-629
+ * as called by prodAppxMSGibbsS :697-700 and `*` :724.
+ *   dimmask   ndens*d bytes, dimmask[j*d+k] != 0 <=> partialDimMask[j][k]; NULL = all active.
+ *   randU/N   injected streams exactly as the reference's keyword arguments (:661-662); when
+ *             randU == NULL both streams come from counter-based Philox4x32-10 keyed by `seed`
+ *             and addressed by (sample, draw) so results do not depend on sharding.
+ *   s0, s1    compute samples s in [s0, s1) of the Np-sample run (0-based); outputs hold only
+ *             that range: points_out d x (s1-s0), indices_out ndens x (s1-s0) (= permutation + 1,
+ *             the reference's label convention, :612-616).
+ */
+int kdeb200_gibbs(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
+                  const uint8_t *dimmask, const double *randU, int64_t nU, const double *randN, int64_t nN,
+                  uint64_t seed, int64_t s0, int64_t s1, double *points_out, int64_t *indices_out);
+/* Same, outputs (and the optional injected streams) in device memory, asynchronous on `stream`. */
+int kdeb200_gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
+                         const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN,
+                         int64_t nN, uint64_t seed, int64_t s0, int64_t s1, double *d_points,
+                         int64_t *d_indices, void *stream);
+/* glbs.Nlevels (src/MSGibbs01.jl:555-568) and the per-sample stream consumption. */
+int kdeb200_gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels,
+                        int64_t *uniforms_per_sample, int64_t *normals_per_sample,
+                        int64_t *kernel_evals_per_sample);
+/* The Philox streams as arrays (what the kernel draws when randU == NULL), for parity tests. */
+int kdeb200_philox_streams(uint64_t seed, int64_t Np, int64_t uniforms_per_sample, int64_t normals_per_sample,
+                           double *randU_out, double *randN_out);
+
+/* ---- S2: brute-force evaluation ------------------------------------------------------------
+ * Replaces evaluate(bd, locations, p, maxErr, addop, diffop) src/DualTree01.jl:303-346 with
+ * FORCE_EVAL_DIRECT (evalDirect :130-162, distGauss! :14-47), i.e. what evaluateDualTree :370-421
+ * and the functor :431-446 compute.  pos is d x M (original order); loo != 0 ignores pos and
+ * evaluates bd at its own points leaving each one out (bd === locations), output in original
+ * point order. */
+int kdeb200_eval(kdeb200_tree_t bd, const double *pos, int64_t M, int loo, int precision, double *p_out);
+int kdeb200_eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int precision, double *d_out,
+                        void *stream);
+
+/* ---- S3: leave-one-out likelihood (fused) --------------------------------------------------
+ * Replaces entropy(bd) src/DualTree01.jl:505-508 / evalAvgLogL :450-470 as called from
+ * nLOO_LL src/CrossValidation.jl:15-24.  bw_var (d variances) overrides the tree's leaf
+ * bandwidth for this call (the caller applies alpha^2 like updateBandwidth! :5-12); NULL keeps
+ * the tree's.  H_out = -(sum_j W_j log L_j), or +Inf under the reference's zero rule. */
+int kdeb200_loo_entropy(kdeb200_tree_t bd, const double *bw_var, double *H_out);
+/* Rows [j0, j1) of the leaf-ordered LOO sum only: partial sum_j W_j log L_j and zero flag, for
+ * the multi-GPU split (all-reduce the two scalars). */
+int kdeb200_loo_partial(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int64_t j1, double *sum_out,
+                        int *zero_flag_out);
+
+/* ---- measurement ----------------------------------------------------------------------------
+ * Pipe-rate microbenchmarks for the roofline denominators: dependent-free DFMA,
+ * FFMA and MUFU.EX2 loops over the whole chip.  which: 0 = DFMA, 1 = FFMA, 2 = MUFU.EX2.
+ * Returns achieved instructions/s (per thread-lane) and the elapsed ms. */
+int kdeb200_pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms);
+/* Milliseconds spent in the kernels of the last call on this thread (CUDA events). */
+int kdeb200_last_kernel_ms(double *ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,260 @@
+// capi.cu -- the extern "C" entry points declared in include/kdeb200.h.
+// Host-buffer variants stage through device memory inside the call (H2D / D2H included), the
+// *_device variants are asynchronous on the caller's stream.
+#include <cmath>
+#include <limits>
+#include <vector>
+
+#include "tree.cuh"
+
+namespace kdeb200 {
+int tree_build_host(int d, int64_t N, const double *points, const double *weights, const double *bw_var,
+                    double *centers, double *ranges, double *wout, double *means, double *bandwidth,
+                    int64_t *left, int64_t *right, int64_t *lowest, int64_t *highest, int64_t *perm);
+int tree_create(int d, int64_t N, const double *means, const double *bandwidth, const double *weights,
+                const int64_t *left, const int64_t *right, const int64_t *perm, kdeb200_tree_t *out);
+int tree_destroy(kdeb200_tree_t t);
+int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int64_t q0, bool scatter,
+                const double *bw_var, double *d_out, cudaStream_t st, int *launches);
+int eval_device_f32(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, double *d_out, cudaStream_t st,
+                    int *launches);
+int loo_partial_device(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int64_t j1, double *d_sum, int *d_flag,
+                       cudaStream_t st, int *launches);
+int gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels, int64_t *perU, int64_t *perN,
+                int64_t *evals);
+int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
+                 const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN, int64_t nN,
+                 uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices, cudaStream_t st,
+                 int *launches);
+int philox_streams_device(uint64_t seed, int64_t Np, int64_t perU, int64_t perN, double *d_U, double *d_G,
+                          cudaStream_t st);
+int pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms_out);
+
+// RAII device buffer on a stream
+struct DevBuf {
+  void *p = nullptr;
+  cudaStream_t st;
+  explicit DevBuf(cudaStream_t s) : st(s) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, st); }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+  template <class T>
+  T *as() { return static_cast<T *>(p); }
+};
+
+struct Timer {  // CUDA-event bracket on the library stream, result readable via kdeb200_last_kernel_ms
+  Context &c;
+  explicit Timer(Context &cc) : c(cc) {
+    c.last_launches = 0;
+    cudaEventRecord(c.ev0, c.stream);
+  }
+  void stop() {
+    cudaEventRecord(c.ev1, c.stream);
+    cudaEventSynchronize(c.ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+    c.last_ms = ms;
+  }
+};
+}  // namespace kdeb200
+
+using namespace kdeb200;
+
+extern "C" {
+
+int kdeb200_tree_build_host(int d, int64_t N, const double *points, const double *weights, const double *bw_var,
+                            double *centers, double *ranges, double *weights_out, double *means, double *bandwidth,
+                            int64_t *left_child, int64_t *right_child, int64_t *lowest_leaf, int64_t *highest_leaf,
+                            int64_t *permutation) {
+  if (!points || !weights || !bw_var || !centers || !ranges || !weights_out || !means || !bandwidth || !left_child ||
+      !right_child || !lowest_leaf || !highest_leaf || !permutation)
+    KDE_FAIL(2, "tree_build_host: NULL argument");
+  return tree_build_host(d, N, points, weights, bw_var, centers, ranges, weights_out, means, bandwidth, left_child,
+                         right_child, lowest_leaf, highest_leaf, permutation);
+}
+
+int kdeb200_tree_create(int d, int64_t N, const double *means, const double *bandwidth, const double *weights,
+                        const int64_t *left_child, const int64_t *right_child, const int64_t *permutation,
+                        kdeb200_tree_t *out) {
+  if (!means || !bandwidth || !weights || !left_child || !right_child || !permutation)
+    KDE_FAIL(2, "tree_create: NULL argument");
+  return tree_create(d, N, means, bandwidth, weights, left_child, right_child, permutation, out);
+}
+
+int kdeb200_tree_destroy(kdeb200_tree_t t) { return tree_destroy(t); }
+
+int kdeb200_tree_info(kdeb200_tree_t t, int *d, int64_t *N, int *nlevels, int64_t *device_bytes) {
+  if (!t) KDE_FAIL(2, "tree_info: NULL tree");
+  if (d) *d = t->d;
+  if (N) *N = t->N;
+  if (nlevels) *nlevels = t->depth;
+  if (device_bytes) *device_bytes = (int64_t)t->device_bytes;
+  return 0;
+}
+
+int kdeb200_gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels, int64_t *uniforms_per_sample,
+                        int64_t *normals_per_sample, int64_t *kernel_evals_per_sample) {
+  if (!trees) KDE_FAIL(2, "gibbs_sizes: NULL trees");
+  return gibbs_sizes(trees, ndens, Niter, nlevels, uniforms_per_sample, normals_per_sample, kernel_evals_per_sample);
+}
+
+int kdeb200_gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
+                         const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN, int64_t nN,
+                         uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices, void *stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!trees || !d_points || !d_indices) KDE_FAIL(2, "gibbs_device: NULL argument");
+  int launches = 0;
+  int rc = gibbs_device(trees, ndens, Np, Niter, add_entropy, dimmask, d_randU, nU, d_randN, nN, seed, s0, s1,
+                        d_points, d_indices, (cudaStream_t)stream, &launches);
+  ctx().last_launches = launches;
+  return rc;
+}
+
+int kdeb200_gibbs(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
+                  const uint8_t *dimmask, const double *randU, int64_t nU, const double *randN, int64_t nN,
+                  uint64_t seed, int64_t s0, int64_t s1, double *points_out, int64_t *indices_out) {
+  if (int rc = ensure_init()) return rc;
+  if (!trees || !points_out || !indices_out) KDE_FAIL(2, "gibbs: NULL argument");
+  Context &c = ctx();
+  int L;
+  int64_t perU, perN;
+  if (int rc = gibbs_sizes(trees, ndens, Niter, &L, &perU, &perN, nullptr)) return rc;
+  if (Np < 0 || s0 < 0 || s1 > Np || s0 > s1) KDE_FAIL(3, "gibbs: bad sample range");
+  const int d = trees[0]->d;
+  const int64_t n = s1 - s0;
+  if (n == 0) return 0;
+  DevBuf dU(c.stream), dN(c.stream), dP(c.stream), dI(c.stream);
+  if ((randU == nullptr) != (randN == nullptr)) KDE_FAIL(3, "gibbs: randU and randN must be given together");
+  if (randU) {
+    // only the slices this range touches travel: [s0*perU - 1, s1*perU - 1) and [s0*perN, s1*perN)
+    if (s1 * perU > nU + 1) KDE_FAIL(7, "gibbs: randU too short (%lld < %lld)", (long long)nU, (long long)(s1 * perU - 1));
+    if (s1 * perN > nN) KDE_FAIL(7, "gibbs: randN too short (%lld < %lld)", (long long)nN, (long long)(s1 * perN));
+    KDE_CUDA(dU.alloc(sizeof(double) * n * perU));
+    KDE_CUDA(dN.alloc(sizeof(double) * n * perN));
+    const int64_t ulo = s0 * perU > 0 ? s0 * perU - 1 : 0;  // slot -1 of sample 0 is never read
+    const int64_t skip = s0 * perU > 0 ? 0 : 1;
+    KDE_CUDA(cudaMemcpyAsync(dU.as<double>() + skip, randU + ulo, sizeof(double) * (n * perU - skip),
+                             cudaMemcpyHostToDevice, c.stream));
+    KDE_CUDA(cudaMemcpyAsync(dN.p, randN + s0 * perN, sizeof(double) * n * perN, cudaMemcpyHostToDevice, c.stream));
+  }
+  KDE_CUDA(dP.alloc(sizeof(double) * d * n));
+  KDE_CUDA(dI.alloc(sizeof(int64_t) * ndens * n));
+  Timer tm(c);
+  int launches = 0;
+  int rc;
+  if (randU) {
+    // device slices are re-based: sample s reads U[(s-s0)*perU + c - 1 + 1] => pass pointer + 1
+    rc = gibbs_device(trees, ndens, n, Niter, add_entropy, dimmask, dU.as<double>() + 1, n * perU - 1,
+                      dN.as<double>(), n * perN, seed, 0, n, dP.as<double>(), dI.as<int64_t>(), c.stream, &launches);
+  } else {
+    rc = gibbs_device(trees, ndens, Np, Niter, add_entropy, dimmask, nullptr, 0, nullptr, 0, seed, s0, s1,
+                      dP.as<double>(), dI.as<int64_t>(), c.stream, &launches);
+  }
+  if (rc) return rc;
+  tm.stop();
+  c.last_launches = launches;
+  KDE_CUDA(cudaMemcpyAsync(points_out, dP.p, sizeof(double) * d * n, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaMemcpyAsync(indices_out, dI.p, sizeof(int64_t) * ndens * n, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int kdeb200_philox_streams(uint64_t seed, int64_t Np, int64_t perU, int64_t perN, double *randU_out,
+                           double *randN_out) {
+  if (int rc = ensure_init()) return rc;
+  if (!randU_out || !randN_out || Np < 0 || perU < 1 || perN < 1) KDE_FAIL(2, "philox_streams: bad argument");
+  Context &c = ctx();
+  DevBuf dU(c.stream), dN(c.stream);
+  KDE_CUDA(dU.alloc(sizeof(double) * Np * perU));
+  KDE_CUDA(dN.alloc(sizeof(double) * Np * perN));
+  if (int rc = philox_streams_device(seed, Np, perU, perN, dU.as<double>(), dN.as<double>(), c.stream)) return rc;
+  KDE_CUDA(cudaMemcpyAsync(randU_out, dU.p, sizeof(double) * Np * perU, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaMemcpyAsync(randN_out, dN.p, sizeof(double) * Np * perN, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int kdeb200_eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int precision, double *d_out,
+                        void *stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!bd || !d_out) KDE_FAIL(2, "eval_device: NULL argument");
+  if (!loo && !d_pos) KDE_FAIL(2, "eval_device: pos is NULL");
+  if (loo) M = bd->N;
+  int launches = 0;
+  int rc;
+  if (precision == KDEB200_F64)
+    rc = eval_device(bd, d_pos, M, loo, 0, true, nullptr, d_out, (cudaStream_t)stream, &launches);
+  else if (precision == KDEB200_F32)
+    rc = eval_device_f32(bd, d_pos, M, loo, d_out, (cudaStream_t)stream, &launches);
+  else
+    KDE_FAIL(3, "eval: unknown precision %d", precision);
+  ctx().last_launches = launches;
+  return rc;
+}
+
+int kdeb200_eval(kdeb200_tree_t bd, const double *pos, int64_t M, int loo, int precision, double *p_out) {
+  if (int rc = ensure_init()) return rc;
+  if (!bd || !p_out) KDE_FAIL(2, "eval: NULL argument");
+  if (!loo && !pos && M > 0) KDE_FAIL(2, "eval: pos is NULL");
+  if (precision != KDEB200_F64 && precision != KDEB200_F32) KDE_FAIL(3, "eval: unknown precision %d", precision);
+  Context &c = ctx();
+  if (loo) M = bd->N;
+  if (M <= 0) return 0;
+  DevBuf dQ(c.stream), dO(c.stream);
+  if (!loo) {
+    KDE_CUDA(dQ.alloc(sizeof(double) * bd->d * M));
+    KDE_CUDA(cudaMemcpyAsync(dQ.p, pos, sizeof(double) * bd->d * M, cudaMemcpyHostToDevice, c.stream));
+  }
+  KDE_CUDA(dO.alloc(sizeof(double) * M));
+  Timer tm(c);
+  int launches = 0;
+  int rc = (precision == KDEB200_F64)
+               ? eval_device(bd, dQ.as<double>(), M, loo, 0, true, nullptr, dO.as<double>(), c.stream, &launches)
+               : eval_device_f32(bd, dQ.as<double>(), M, loo, dO.as<double>(), c.stream, &launches);
+  if (rc) return rc;
+  tm.stop();
+  c.last_launches = launches;
+  KDE_CUDA(cudaMemcpyAsync(p_out, dO.p, sizeof(double) * M, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int kdeb200_loo_partial(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int64_t j1, double *sum_out,
+                        int *zero_flag_out) {
+  if (int rc = ensure_init()) return rc;
+  if (!bd || !sum_out || !zero_flag_out) KDE_FAIL(2, "loo_partial: NULL argument");
+  if (j0 < 0 || j1 > bd->N || j0 > j1) KDE_FAIL(3, "loo_partial: bad row range");
+  Context &c = ctx();
+  *sum_out = 0.0;
+  *zero_flag_out = 0;
+  if (j0 == j1) return 0;
+  DevBuf dS(c.stream), dF(c.stream);
+  KDE_CUDA(dS.alloc(sizeof(double)));
+  KDE_CUDA(dF.alloc(sizeof(int)));
+  Timer tm(c);
+  int launches = 0;
+  if (int rc = loo_partial_device(bd, bw_var, j0, j1, dS.as<double>(), dF.as<int>(), c.stream, &launches)) return rc;
+  tm.stop();
+  c.last_launches = launches;
+  KDE_CUDA(cudaMemcpyAsync(sum_out, dS.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaMemcpyAsync(zero_flag_out, dF.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int kdeb200_loo_entropy(kdeb200_tree_t bd, const double *bw_var, double *H_out) {
+  if (!bd || !H_out) KDE_FAIL(2, "loo_entropy: NULL argument");
+  double s = 0.0;
+  int flag = 0;
+  if (int rc = kdeb200_loo_partial(bd, bw_var, 0, bd->N, &s, &flag)) return rc;
+  // evalAvgLogL returns -Inf under the zero rule; entropy = -evalAvgLogL
+  *H_out = flag ? std::numeric_limits<double>::infinity() : -s;
+  return 0;
+}
+
+int kdeb200_pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms) {
+  return pipe_peak(which, iters, lane_ops_per_s, ms);
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// common.cuh -- shared host/device helpers of libkdeb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/kdeb200.h"
+
+namespace kdeb200 {
+
+// ---------------------------------------------------------------- errors ----------------
+void set_error(const char *fmt, ...);
+const char *get_error();
+
+#define KDE_CUDA(call)                                                                             \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      ::kdeb200::set_error("%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return 100 + (int)e__;                                                                       \
+    }                                                                                              \
+  } while (0)
+
+#define KDE_FAIL(code, ...)             \
+  do {                                  \
+    ::kdeb200::set_error(__VA_ARGS__); \
+    return (code);                      \
+  } while (0)
+
+// ---------------------------------------------------------------- context ---------------
+struct Context {
+  bool ready = false;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  double *d_exptab = nullptr;  // 64-entry 2^(j/64) table
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_ms = 0.0;
+  int last_launches = 0;
+};
+Context &ctx();
+int ensure_init();
+
+// ---------------------------------------------------------------- Philox4x32-10 ---------
+// Counter-based generator (Salmon et al., SC'11).  Streams are addressed as
+//   uniform(sample s, draw c)  : counter = (c_lo, c_hi | 0<<31.., s_lo, s_hi), stream tag 0
+//   normal (sample s, slot q)  : stream tag 1
+// so the variates a chain consumes do not depend on how samples are sharded across GPUs.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                        uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0;
+    const uint64_t p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0;
+    k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// uniform in [0,1) with 53 random bits, like Julia's rand()
+__host__ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t sample, uint32_t draw) {
+  uint32_t o[4];
+  philox4x32_10(draw, 0u, (uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  const uint64_t bits = ((uint64_t)o[0] << 32) | o[1];
+  return (double)(bits >> 11) * 0x1.0p-53;
+}
+
+#ifdef __CUDACC__
+// standard normal by Box-Muller (device only: the host never generates normals itself --
+// kdeb200_philox_streams runs this same code on the GPU so tests see bit-identical values)
+__device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t sample, uint32_t slot) {
+  uint32_t o[4];
+  philox4x32_10(slot, 1u, (uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  const uint64_t b1 = ((uint64_t)o[0] << 32) | o[1];
+  const uint64_t b2 = ((uint64_t)o[2] << 32) | o[3];
+  const double u1 = ((double)(b1 >> 11) + 0.5) * 0x1.0p-53;  // (0,1)
+  const double u2 = (double)(b2 >> 11) * 0x1.0p-53;          // [0,1)
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// ---------------------------------------------------------------- FP64 exp --------------
+// exp(x) = 2^(n/64 >> 6) * T[n & 63] * e^r,  n = rint(x*64/ln2), |r| <= ln2/128.
+// 10 FP64-pipe instructions (stock exp(): 14 DFMA + 2 DADD + 1 DMUL) + one shared-memory
+// table load; truncation error r^6/720 <= 3.5e-17, total error ~1 ulp.  |x| > 700 (results
+// near the subnormal / overflow range) takes the libdevice path so denormals match IEEE.
+#define KDE_EXP_TAB 64
+__device__ __forceinline__ double kde_exp(double x, const double *__restrict__ tab) {
+  const double L2E64 = 92.33248261689366;            // 64/ln2
+  const double C1 = 1.0830424696249145e-02;          // ln2/64 (rounded)
+  const double C2 = 3.623510646634843e-19;           // ln2/64 - C1 (residual, from 60-digit ln2)
+  const double SHIFT = 6755399441055744.0;           // 1.5 * 2^52
+  double y;
+  if (fabs(x) <= 700.0) {
+    const double t = __fma_rn(x, L2E64, SHIFT);
+    const int n = __double2loint(t);
+    const double nf = __dadd_rn(t, -SHIFT);
+    double r = __fma_rn(nf, -C1, x);
+    r = __fma_rn(nf, -C2, r);
+    double q = __fma_rn(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    q = __fma_rn(q, r, 1.6666666666666666e-01);
+    q = __fma_rn(q, r, 0.5);
+    const double r2 = __dmul_rn(r, r);
+    const double p = __fma_rn(q, r2, r);
+    const double T = tab[n & (KDE_EXP_TAB - 1)];
+    y = __fma_rn(T, p, T);
+    y = __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
+  } else {
+    y = exp(x);
+  }
+  return y;
+}
+
+// ---------------------------------------------------------------- TMA bulk + mbarrier ---
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit (SASS: UBLKCP), completion on an mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace kdeb200

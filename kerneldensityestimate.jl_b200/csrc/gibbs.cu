@@ -1,0 +1,654 @@
+// gibbs.cu -- K1: the multiscale Gibbs KDE-product sampler as one kernel.
+//
+// Computes what gibbs1 (src/MSGibbs01.jl:527-629) computes for every output sample:
+// levelInit!/initIndices! :467-497, samplePoint! :440-463 (gaussianProductMeanCov! :176-216),
+// levelDown! :500-523, sampleIndices! :364-385, sampleIndex :404-429 (makeFasterSampleIndex!
+// :250-328, selectLabelOnLevel :330-351, updateGlbParticlesVariance! :89-115), labels :612-616.
+//
+// Mapping (DESIGN.md "K1"): ONE THREAD PER CHAIN.  All chains execute the same static schedule
+// of label draws (level, pass, density), so a CTA streams each level's node records once through
+// a 3-stage shared-memory ring filled by 1-D TMA bulk copies and every lane reads the same record
+// (broadcast LDS).  A draw is two passes: pass 1 accumulates the unnormalised weights p[z]
+// SEQUENTIALLY in the reference's node order (identical summation order => identical pT and CDF
+// up to exp rounding) and checkpoints the running sum every G nodes (<= 64 checkpoints, local
+// memory); pass 2 re-evaluates only the chunk that contains u * pT, from global memory.
+// The arithmetic of one kernel evaluation is restructured:
+//   leaf levels (uniform bandwidth): 1/c_k and the normaliser hoisted out of the node loop,
+//     ln w folded into the exponent                       -> 3d + 11 FP64-pipe instr / node
+//   internal levels, sampleIndices!: -0.5/b_k and ln w - 0.5 sum ln b_k precomputed per node
+//   internal levels, sampleIndex   : c_k = b_k + Calmost_k, sum_k ln c_k -> one rsqrt(prod c_k)
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "tree.cuh"
+
+namespace kdeb200 {
+
+constexpr int GB_THREADS = 128;
+constexpr int GB_STAGES = 3;
+constexpr int GB_TILE_BYTES = 8192;
+constexpr int GB_MAXCK = 64;  // checkpoints per draw
+
+enum : int { VAR_A = 0, VAR_B = 1, VAR_C = 2 };
+
+struct alignas(16) Draw {
+  const double *rec;        // evaluation records of this level (variant-specific layout)
+  const double *rec_state;  // records the chain state is refreshed from ([m.., lnw] or [m.., b.., lnw])
+  const double *wts;        // raw weights (fallback path)
+  int n;                    // nodes on the level
+  int stride;               // doubles per evaluation record
+  int state_stride;
+  int G;                    // checkpoint chunk (power of two)
+  int nchunks;
+  int tnodes;               // nodes per tile (power of two)
+  int ntiles;
+  int tile0;                // first tile of this draw in the per-sample tile stream
+  short j;                  // density
+  signed char variant;      // VAR_A / VAR_B / VAR_C
+  signed char kind;         // 0: sampleIndices! (against X), 1: sampleIndex (leave-one-out product)
+  signed char state_has_bw; // rec_state carries per-node variances
+  signed char new_level;    // first draw of a level: samplePoint! comes first
+  short level;              // 1-based level
+};
+
+struct alignas(16) TileDesc {
+  const double *src;
+  uint32_t bytes;
+  uint32_t pad;
+};
+
+struct GibbsParams {
+  const Draw *draws;
+  const TileDesc *tiles;
+  const double *exptab;
+  const double *randU, *randN;  // injected streams or null (Philox)
+  double *points;               // d x (s1-s0)
+  int64_t *indices;             // M x (s1-s0)
+  int64_t s0, s1, perU, perN;
+  uint64_t seed;
+  int ndraws, ntiles, M, L, T, add_entropy, nbatches;
+  const double *root_rec[KDEB200_MAX_DENS];  // [m.., b.., lnw] of node 1
+  const int64_t *labels[KDEB200_MAX_DENS];   // deepest level: permutation + 1
+  double hvar[KDEB200_MAX_DENS][KDEB200_MAX_DIM];
+  unsigned char mask[KDEB200_MAX_DENS][KDEB200_MAX_DIM];   // partialDimMask[j][k]
+  unsigned char other[KDEB200_MAX_DENS][KDEB200_MAX_DIM];  // OR_{i != j} mask[i][k]
+};
+
+// ---- one kernel evaluation, three record layouts -----------------------------------------
+// Explicit rn intrinsics: pass 1 and pass 2 must produce bit-identical p[z].
+template <int D, bool MASK>
+struct Hoist {
+  double mu[D];    // X or Malmost
+  double ich[D];   // variant A: -0.5 / (h_k + Calmost_k)
+  double cadd[D];  // variant C: Calmost_k
+  bool act[D];     // dimension participates (partialDimMask logic, :270-285)
+};
+
+template <int D, bool MASK>
+__device__ __forceinline__ double eval_A(const double *__restrict__ r, const Hoist<D, MASK> &h,
+                                         const double *__restrict__ tab) {
+  double acc = r[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    if (MASK && !h.act[k]) continue;
+    const double df = __dadd_rn(r[k], -h.mu[k]);
+    acc = __fma_rn(__dmul_rn(df, df), h.ich[k], acc);
+  }
+  return kde_exp(acc, tab);
+}
+
+template <int D, bool MASK>
+__device__ __forceinline__ double eval_B(const double *__restrict__ r, const Hoist<D, MASK> &h,
+                                         const double *__restrict__ tab) {
+  double acc = r[2 * D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double df = __dadd_rn(r[k], -h.mu[k]);
+    acc = __fma_rn(__dmul_rn(df, df), r[D + k], acc);
+  }
+  return kde_exp(acc, tab);
+}
+
+template <int D, bool MASK>
+__device__ __forceinline__ double eval_C(const double *__restrict__ r, const Hoist<D, MASK> &h,
+                                         const double *__restrict__ tab) {
+  double acc = r[2 * D];
+  double prod = 1.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    if (MASK && !h.act[k]) continue;
+    const double c = __dadd_rn(r[D + k], h.cadd[k]);
+    const double df = __dadd_rn(r[k], -h.mu[k]);
+    const double q = __dmul_rn(__dmul_rn(df, df), -0.5);
+    acc = __fma_rn(q, __drcp_rn(c), acc);
+    prod = __dmul_rn(prod, c);
+  }
+  return __dmul_rn(kde_exp(acc, tab), rsqrt(prod));
+}
+
+template <int D, bool MASK, int VAR>
+__device__ __forceinline__ double eval_node(const double *__restrict__ r, const Hoist<D, MASK> &h,
+                                            const double *__restrict__ tab) {
+  if (VAR == VAR_A) return eval_A<D, MASK>(r, h, tab);
+  if (VAR == VAR_B) return eval_B<D, MASK>(r, h, tab);
+  return eval_C<D, MASK>(r, h, tab);
+}
+
+// pass 1 over the tiles of one draw: sequential sum, checkpoints every G nodes
+struct Ring {
+  double *tiles;
+  uint64_t *bars;
+  const TileDesc *descs;
+  int64_t total;  // tiles this CTA will consume over its whole life
+  int ntiles;     // tiles per sample schedule
+};
+
+__device__ __forceinline__ void ring_issue(const Ring &R, int64_t q) {
+  const TileDesc td = R.descs[(int)(q % R.ntiles)];
+  uint64_t *bar = &R.bars[q % GB_STAGES];
+  mbar_expect_tx(bar, td.bytes);
+  tma_bulk_g2s(R.tiles + (size_t)(q % GB_STAGES) * (GB_TILE_BYTES / 8), td.src, td.bytes, bar);
+}
+
+template <int D, bool MASK, int VAR>
+__device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h, const double *__restrict__ tab,
+                                        const Ring &R, int64_t &q, double *__restrict__ ck) {
+  const int stride = dr.stride;
+  const int step = dr.G < dr.tnodes ? dr.G : dr.tnodes;
+  double S = 0.0;
+  int c = 0;
+  int done = 0;
+  for (int t = 0; t < dr.ntiles; ++t, ++q) {
+    const int cnt = (dr.n - done < dr.tnodes) ? (dr.n - done) : dr.tnodes;
+    mbar_wait(&R.bars[q % GB_STAGES], (uint32_t)((q / GB_STAGES) & 1));
+    const double *rec = R.tiles + (size_t)(q % GB_STAGES) * (GB_TILE_BYTES / 8);
+    for (int z0 = 0; z0 < cnt; z0 += step) {
+      const int m = (cnt - z0 < step) ? (cnt - z0) : step;
+      const double *r = rec + (size_t)z0 * stride;
+      int z = 0;
+      for (; z + 4 <= m; z += 4) {
+        const double p0 = eval_node<D, MASK, VAR>(r, h, tab);
+        const double p1 = eval_node<D, MASK, VAR>(r + stride, h, tab);
+        const double p2 = eval_node<D, MASK, VAR>(r + 2 * stride, h, tab);
+        const double p3 = eval_node<D, MASK, VAR>(r + 3 * stride, h, tab);
+        S = __dadd_rn(S, p0);
+        S = __dadd_rn(S, p1);
+        S = __dadd_rn(S, p2);
+        S = __dadd_rn(S, p3);
+        r += 4 * stride;
+      }
+      for (; z < m; ++z) {
+        S = __dadd_rn(S, eval_node<D, MASK, VAR>(r, h, tab));
+        r += stride;
+      }
+      const int upto = done + z0 + m;  // nodes consumed so far
+      if ((upto & (dr.G - 1)) == 0 || upto == dr.n) ck[c++] = S;
+    }
+    done += cnt;
+    __syncthreads();  // stage free again
+    if (threadIdx.x == 0 && q + GB_STAGES < R.total) ring_issue(R, q + GB_STAGES);
+  }
+  return S;
+}
+
+// pass 2: locate the first z with target <= prefix(z) inside chunk cs (per-lane global loads)
+template <int D, bool MASK, int VAR>
+__device__ __forceinline__ int pass2(const Draw &dr, const Hoist<D, MASK> &h, const double *__restrict__ tab, int cs,
+                                  double S, double target) {
+  const int z0 = cs * dr.G;
+  const int z1 = (z0 + dr.G < dr.n) ? z0 + dr.G : dr.n;
+  const double *r = dr.rec + (size_t)z0 * dr.stride;
+  int zs = z1 - 1;
+  bool found = false;
+  for (int z = z0; z < z1; ++z) {
+    S = __dadd_rn(S, eval_node<D, MASK, VAR>(r, h, tab));
+    if (!found && target <= S) {
+      zs = z;
+      found = true;
+    }
+    r += dr.stride;
+  }
+  return zs;
+}
+
+template <int D, bool MASK>
+__global__ void __launch_bounds__(GB_THREADS, 4) gibbs_kernel(const __grid_constant__ GibbsParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tiles = reinterpret_cast<double *>(smem_raw);
+  double *tab = reinterpret_cast<double *>(smem_raw + GB_STAGES * GB_TILE_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + GB_STAGES * GB_TILE_BYTES + KDE_EXP_TAB * 8);
+  const int tid = threadIdx.x;
+  const int M = P.M;
+
+  if (tid < KDE_EXP_TAB) tab[tid] = P.exptab[tid];
+  if (tid == 0) {
+    for (int s = 0; s < GB_STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  int nb_local = 0;
+  for (int b = blockIdx.x; b < P.nbatches; b += gridDim.x) ++nb_local;
+  Ring R;
+  R.tiles = tiles;
+  R.bars = bars;
+  R.descs = P.tiles;
+  R.ntiles = P.ntiles;
+  R.total = (int64_t)nb_local * P.ntiles;
+  if (tid == 0)
+    for (int64_t q0 = 0; q0 < GB_STAGES && q0 < R.total; ++q0) ring_issue(R, q0);
+  int64_t q = 0;
+
+  // chain state: lambda = 1/variance and lambda*mu of the currently selected node of each density
+  double lam[KDEB200_MAX_DENS * D];
+  double lmu[KDEB200_MAX_DENS * D];
+  double ck[GB_MAXCK];
+  int selpos[KDEB200_MAX_DENS];
+
+  for (int batch = blockIdx.x; batch < P.nbatches; batch += gridDim.x) {
+    int64_t s = P.s0 + (int64_t)batch * GB_THREADS + tid;
+    const bool live = s < P.s1;
+    if (!live) s = P.s1 - 1;  // idle lanes replay the last chain (keeps the CTA in lock-step)
+
+    // levelInit!/initIndices!/calcIndices!: every density starts at the root
+    for (int j = 0; j < M; ++j) {
+      const double *rr = P.root_rec[j];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        if (MASK && !P.mask[j][k]) {
+          lam[j * D + k] = 0.0;
+          lmu[j * D + k] = 0.0;
+        } else {
+          const double l = 1.0 / rr[D + k];
+          lam[j * D + k] = l;
+          lmu[j * D + k] = rr[k] * l;
+        }
+      }
+      selpos[j] = 0;
+    }
+
+    double X[D];
+    for (int di = 0; di < P.ndraws; ++di) {
+      const Draw dr = P.draws[di];
+      const int j = dr.j;
+
+      if (dr.new_level) {  // samplePoint!(addEntropy = true) with normals g(level-1, k)
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double Lm = 0.0, Hm = 0.0;
+          bool any = !MASK;
+          for (int i = 0; i < M; ++i) {
+            if (MASK && P.mask[i][k]) any = true;
+            Lm += lam[i * D + k];
+            Hm += lmu[i * D + k];
+          }
+          const uint32_t slot = (uint32_t)((dr.level - 1) * D + k);
+          const double g = P.randN ? P.randN[s * P.perN + slot] : philox_normal(P.seed, (uint64_t)s, slot);
+          if (any) {
+            const double cov = 1.0 / Lm;
+            X[k] = cov * Hm + sqrt(cov) * g;
+          } else {
+            X[k] = 0.0;
+          }
+        }
+      }
+
+      Hoist<D, MASK> h;
+      double scale = 1.0;  // normaliser common to the whole level (variant A), for the 1e-99 test
+      if (dr.kind == 0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          h.mu[k] = X[k];
+          h.cadd[k] = 0.0;
+          h.act[k] = MASK ? (P.mask[j][k] && P.other[j][k]) : true;
+        }
+      } else {  // leave-one-out product of the other densities' selected kernels
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double Lm = 0.0, Hm = 0.0;
+          for (int i = 0; i < M; ++i) {
+            if (i == j) continue;
+            Lm += lam[i * D + k];
+            Hm += lmu[i * D + k];
+          }
+          const bool oth = MASK ? (P.other[j][k] != 0) : (M > 1);
+          if (oth) {
+            const double cov = 1.0 / Lm;
+            h.cadd[k] = cov;
+            h.mu[k] = cov * Hm;
+          } else {
+            h.cadd[k] = 0.0;
+            h.mu[k] = 0.0;
+          }
+          h.act[k] = (MASK ? (P.mask[j][k] != 0) : true) && oth;
+        }
+      }
+      if (dr.variant == VAR_A) {
+        double prod = 1.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double c = P.hvar[j][k] + h.cadd[k];
+          h.ich[k] = -0.5 / c;
+          if (!MASK || h.act[k]) prod *= c;
+        }
+        scale = rsqrt(prod);
+      }
+
+      double pT;
+      if (dr.variant == VAR_A)
+        pT = pass1<D, MASK, VAR_A>(dr, h, tab, R, q, ck);
+      else if (dr.variant == VAR_B)
+        pT = pass1<D, MASK, VAR_B>(dr, h, tab, R, q, ck);
+      else
+        pT = pass1<D, MASK, VAR_C>(dr, h, tab, R, q, ck);
+
+      // selectLabelOnLevel: the c-th call of this chain reads randU[(s*perU + c) - 1]
+      int zs = 0;
+      if (dr.n > 1) {
+        const uint32_t c = (uint32_t)(M + di);
+        const double u = P.randU ? P.randU[s * P.perU + c - 1] : philox_uniform(P.seed, (uint64_t)s, c);
+        if (pT * scale < 1e-99) {  // :311-315: all p[z] = weight(last node)
+          const double w = dr.wts[dr.n - 1];
+          double tot = 0.0;
+          for (int z = 0; z < dr.n; ++z) tot += w;
+          const double qv = w / tot;
+          double cdf = 0.0;
+          zs = dr.n - 1;
+          bool found = false;
+          for (int z = 0; z < dr.n - 1; ++z) {
+            cdf += qv;
+            if (!found && u <= cdf) {
+              zs = z;
+              found = true;
+            }
+          }
+        } else {
+          const double target = u * pT;
+          int lo = 0, hi = dr.nchunks;  // first chunk whose end-prefix reaches the target
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (target <= ck[mid]) hi = mid; else lo = mid + 1;
+          }
+          if (lo >= dr.nchunks) {
+            zs = dr.n - 1;
+          } else if (dr.G == 1) {
+            zs = lo;
+          } else {
+            const double S0 = lo > 0 ? ck[lo - 1] : 0.0;
+            if (dr.variant == VAR_A)
+              zs = pass2<D, MASK, VAR_A>(dr, h, tab, lo, S0, target);
+            else if (dr.variant == VAR_B)
+              zs = pass2<D, MASK, VAR_B>(dr, h, tab, lo, S0, target);
+            else
+              zs = pass2<D, MASK, VAR_C>(dr, h, tab, lo, S0, target);
+          }
+        }
+      }
+      selpos[j] = zs;
+
+      // updateGlbParticlesVariance!(j)
+      {
+        const double *rs = dr.rec_state + (size_t)zs * dr.state_stride;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          if (MASK && !P.mask[j][k]) {
+            lam[j * D + k] = 0.0;
+            lmu[j * D + k] = 0.0;
+          } else {
+            const double var = dr.state_has_bw ? rs[D + k] : P.hvar[j][k];
+            const double l = 1.0 / var;
+            lam[j * D + k] = l;
+            lmu[j * D + k] = rs[k] * l;
+          }
+        }
+      }
+    }
+
+    // labels (:612-616) and the final samplePoint! (:625)
+    if (live) {
+      const int64_t o = s - P.s0;
+      for (int j = 0; j < M; ++j) P.indices[o * M + j] = P.labels[j][selpos[j]];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double Lm = 0.0, Hm = 0.0;
+        bool any = !MASK;
+        for (int i = 0; i < M; ++i) {
+          if (MASK && P.mask[i][k]) any = true;
+          Lm += lam[i * D + k];
+          Hm += lmu[i * D + k];
+        }
+        double v = 0.0;
+        if (any) {
+          const double cov = 1.0 / Lm;
+          v = cov * Hm;
+          if (P.add_entropy) {
+            const uint32_t slot = (uint32_t)(P.L * D + k);
+            const double g = P.randN ? P.randN[s * P.perN + slot] : philox_normal(P.seed, (uint64_t)s, slot);
+            v = v + sqrt(cov) * g;
+          }
+        }
+        P.points[o * D + k] = v;
+      }
+    }
+  }
+}
+
+__global__ void philox_streams_kernel(uint64_t seed, int64_t Np, int64_t perU, int64_t perN, double *U, double *G) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nu = Np * perU, nn = Np * perN;
+  if (i < nu) {
+    // array slot g (0-based) is read by sample s = (g+1) / perU at call c = (g+1) % perU
+    const int64_t g1 = i + 1;
+    U[i] = philox_uniform(seed, (uint64_t)(g1 / perU), (uint32_t)(g1 % perU));
+  }
+  if (i < nn) G[i] = philox_normal(seed, (uint64_t)(i / perN), (uint32_t)(i % perN));
+}
+
+// ---------------------------------------------------------------- host side --------------
+int gibbs_nlevels(const kdeb200_tree_t *trees, int ndens) {
+  int64_t maxNp = 0;
+  for (int j = 0; j < ndens; ++j)
+    if (maxNp < trees[j]->N) maxNp = trees[j]->N;
+  return (int)std::floor((std::log((double)maxNp) / std::log(2.0)) + 1.0);  // src/MSGibbs01.jl:568
+}
+
+struct Schedule {
+  std::vector<Draw> draws;
+  std::vector<TileDesc> tiles;
+  int64_t evals = 0;
+};
+
+static void build_schedule(const kdeb200_tree_t *trees, int M, int L, int T, bool masked, Schedule &S) {
+  for (int l = 1; l <= L; ++l) {
+    for (int pass = 0; pass <= T; ++pass) {
+      for (int j = 0; j < M; ++j) {
+        const kdeb200_tree_s *t = trees[j];
+        const Level &lv = t->levels[l < t->depth ? l : t->depth];
+        Draw dr;
+        std::memset(&dr, 0, sizeof(dr));
+        dr.j = (short)j;
+        dr.kind = pass == 0 ? 0 : 1;
+        dr.level = (short)l;
+        dr.new_level = (pass == 0 && j == 0) ? 1 : 0;
+        dr.n = (int)lv.n;
+        dr.wts = t->d_buf + lv.offW;
+        if (lv.cls == 0) {
+          dr.variant = VAR_A;
+          dr.rec = t->d_buf + lv.offA;
+          dr.stride = t->SA;
+          dr.rec_state = dr.rec;
+          dr.state_stride = t->SA;
+          dr.state_has_bw = 0;
+        } else {
+          dr.variant = (pass == 0 && !masked) ? VAR_B : VAR_C;
+          dr.rec = t->d_buf + (dr.variant == VAR_B ? lv.offB : lv.offC);
+          dr.stride = t->SC;
+          dr.rec_state = t->d_buf + lv.offC;
+          dr.state_stride = t->SC;
+          dr.state_has_bw = 1;
+        }
+        int G = 1;
+        while ((int64_t)G * GB_MAXCK < lv.n) G *= 2;
+        dr.G = G;
+        dr.nchunks = (int)((lv.n + G - 1) / G);
+        int tn = 1;
+        while (tn * 2 * dr.stride * 8 <= GB_TILE_BYTES) tn *= 2;
+        dr.tnodes = tn;
+        dr.ntiles = (int)((lv.n + tn - 1) / tn);
+        dr.tile0 = (int)S.tiles.size();
+        for (int q = 0; q < dr.ntiles; ++q) {
+          const int64_t a = (int64_t)q * tn;
+          const int64_t cnt = (lv.n - a < tn) ? (lv.n - a) : tn;
+          TileDesc td;
+          td.src = dr.rec + a * dr.stride;
+          td.bytes = (uint32_t)(cnt * dr.stride * sizeof(double));
+          td.pad = 0;
+          S.tiles.push_back(td);
+        }
+        S.evals += lv.n;
+        S.draws.push_back(dr);
+      }
+    }
+  }
+}
+
+template <int D>
+static cudaError_t launch_gibbs_d(const GibbsParams &P, bool masked, int grid_cap, size_t smem, cudaStream_t st,
+                                  int sm_count) {
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GB_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int grid = per_sm * sm_count;
+    if (grid > grid_cap) grid = grid_cap;
+    kern<<<grid, GB_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+  };
+  return masked ? launch(gibbs_kernel<D, true>) : launch(gibbs_kernel<D, false>);
+}
+
+int gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels, int64_t *perU, int64_t *perN,
+                int64_t *evals) {
+  if (ndens < 1 || ndens > KDEB200_MAX_DENS) KDE_FAIL(3, "gibbs: ndens=%d outside 1..%d", ndens, KDEB200_MAX_DENS);
+  if (Niter < 0) KDE_FAIL(3, "gibbs: Niter must be >= 0");
+  for (int j = 0; j < ndens; ++j) {
+    if (!trees[j]) KDE_FAIL(3, "gibbs: tree %d is NULL", j);
+    if (trees[j]->d != trees[0]->d) KDE_FAIL(6, "kdes must have same dimension");  // src/MSGibbs01.jl:721
+  }
+  const int L = gibbs_nlevels(trees, ndens);
+  if (nlevels) *nlevels = L;
+  if (perU) *perU = (int64_t)ndens * (1 + (int64_t)L * (1 + Niter));
+  if (perN) *perN = (int64_t)trees[0]->d * (L + 1);
+  if (evals) {
+    int64_t e = 0;
+    for (int j = 0; j < ndens; ++j)
+      for (int l = 1; l <= L; ++l) e += trees[j]->levels[l < trees[j]->depth ? l : trees[j]->depth].n;
+    *evals = e * (1 + Niter);
+  }
+  return 0;
+}
+
+int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
+                 const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN, int64_t nN,
+                 uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices, cudaStream_t st,
+                 int *launches) {
+  Context &c = ctx();
+  int L = 0;
+  int64_t perU = 0, perN = 0;
+  if (int rc = gibbs_sizes(trees, ndens, Niter, &L, &perU, &perN, nullptr)) return rc;
+  const int d = trees[0]->d;
+  if (Np < 0 || s0 < 0 || s1 > Np || s0 > s1) KDE_FAIL(3, "gibbs: bad sample range [%lld,%lld) of %lld", (long long)s0, (long long)s1, (long long)Np);
+  if (s1 == s0) return 0;
+  if ((d_randU == nullptr) != (d_randN == nullptr)) KDE_FAIL(3, "gibbs: randU and randN must be given together");
+  if (d_randU) {  // the reference would throw BoundsError
+    if (s1 * perU > nU + 1) KDE_FAIL(7, "gibbs: randU too short (%lld < %lld)", (long long)nU, (long long)(s1 * perU - 1));
+    if (s1 * perN > nN) KDE_FAIL(7, "gibbs: randN too short (%lld < %lld)", (long long)nN, (long long)(s1 * perN));
+  }
+  for (int j = 0; j < ndens; ++j)
+    if (trees[j]->degenerate)
+      KDE_FAIL(8, "gibbs: density %d has a non-positive or non-finite bandwidth/mean; not supported on the GPU path (no CPU fallback)", j + 1);
+
+  GibbsParams P;
+  std::memset(&P, 0, sizeof(P));
+  bool masked = (ndens == 1);  // a lone density has no "other" dims: handled by the mask logic
+  for (int j = 0; j < ndens; ++j)
+    for (int k = 0; k < d; ++k) {
+      P.mask[j][k] = dimmask ? (dimmask[j * d + k] != 0) : 1;
+      if (!P.mask[j][k]) masked = true;
+    }
+  for (int j = 0; j < ndens; ++j)
+    for (int k = 0; k < d; ++k) {
+      unsigned char o = 0;
+      for (int i = 0; i < ndens; ++i)
+        if (i != j && P.mask[i][k]) o = 1;
+      P.other[j][k] = o;
+    }
+  Schedule S;
+  build_schedule(trees, ndens, L, Niter, masked, S);
+
+  Draw *d_draws = nullptr;
+  TileDesc *d_tiles = nullptr;
+  KDE_CUDA(cudaMallocAsync(&d_draws, sizeof(Draw) * S.draws.size(), st));
+  KDE_CUDA(cudaMallocAsync(&d_tiles, sizeof(TileDesc) * S.tiles.size(), st));
+  KDE_CUDA(cudaMemcpyAsync(d_draws, S.draws.data(), sizeof(Draw) * S.draws.size(), cudaMemcpyHostToDevice, st));
+  KDE_CUDA(cudaMemcpyAsync(d_tiles, S.tiles.data(), sizeof(TileDesc) * S.tiles.size(), cudaMemcpyHostToDevice, st));
+  KDE_CUDA(cudaStreamSynchronize(st));  // S's vectors are pageable host memory
+
+  P.draws = d_draws;
+  P.tiles = d_tiles;
+  P.exptab = c.d_exptab;
+  P.randU = d_randU;
+  P.randN = d_randN;
+  P.points = d_points;
+  P.indices = d_indices;
+  P.s0 = s0;
+  P.s1 = s1;
+  P.perU = perU;
+  P.perN = perN;
+  P.seed = seed;
+  P.ndraws = (int)S.draws.size();
+  P.ntiles = (int)S.tiles.size();
+  P.M = ndens;
+  P.L = L;
+  P.T = Niter;
+  P.add_entropy = add_entropy ? 1 : 0;
+  P.nbatches = (int)((s1 - s0 + GB_THREADS - 1) / GB_THREADS);
+  for (int j = 0; j < ndens; ++j) {
+    const kdeb200_tree_s *t = trees[j];
+    P.root_rec[j] = t->d_buf + t->levels[0].offC;
+    P.labels[j] = t->d_labels;
+    for (int k = 0; k < d; ++k) P.hvar[j][k] = t->hvar[k];
+  }
+  const size_t smem = GB_STAGES * GB_TILE_BYTES + KDE_EXP_TAB * 8 + GB_STAGES * 8;
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (d) {
+    case 1: e = launch_gibbs_d<1>(P, masked, P.nbatches, smem, st, c.sm_count); break;
+    case 2: e = launch_gibbs_d<2>(P, masked, P.nbatches, smem, st, c.sm_count); break;
+    case 3: e = launch_gibbs_d<3>(P, masked, P.nbatches, smem, st, c.sm_count); break;
+    case 4: e = launch_gibbs_d<4>(P, masked, P.nbatches, smem, st, c.sm_count); break;
+    case 5: e = launch_gibbs_d<5>(P, masked, P.nbatches, smem, st, c.sm_count); break;
+    case 6: e = launch_gibbs_d<6>(P, masked, P.nbatches, smem, st, c.sm_count); break;
+    case 7: e = launch_gibbs_d<7>(P, masked, P.nbatches, smem, st, c.sm_count); break;
+    case 8: e = launch_gibbs_d<8>(P, masked, P.nbatches, smem, st, c.sm_count); break;
+  }
+  if (e != cudaSuccess) KDE_FAIL(100 + (int)e, "gibbs kernel launch: %s", cudaGetErrorString(e));
+  if (launches) *launches += 1;
+  KDE_CUDA(cudaFreeAsync(d_draws, st));
+  KDE_CUDA(cudaFreeAsync(d_tiles, st));
+  return 0;
+}
+
+int philox_streams_device(uint64_t seed, int64_t Np, int64_t perU, int64_t perN, double *d_U, double *d_G,
+                          cudaStream_t st) {
+  const int64_t n = (Np * perU > Np * perN) ? Np * perU : Np * perN;
+  if (n <= 0) return 0;
+  philox_streams_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seed, Np, perU, perN, d_U, d_G);
+  KDE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace kdeb200

@@ -1,0 +1,330 @@
+// tree.cu -- K3: host construction of the reference's tree arrays and the flatten/upload of a
+// BallTreeDensity into level-ordered device records.
+//
+// Behaviour follows (restated, not copied) src/BallTree01.jl:142-173 (most_spread_coord),
+// :223-242 (select!), :282-336 (calcStatsBall!), :342-463 (buildBall!/buildTree!/makeBallTree),
+// src/BallTreeDensity01.jl:141-231 (calcStatsDensity!, makeBallTreeDensity).  Unlike the
+// reference, which swaps every per-leaf array on each partition step, the partition here
+// runs on one index permutation and gathers the leaf payload once; node statistics are
+// computed afterwards in the recorded post-order.  The resulting arrays are identical.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "tree.cuh"
+
+namespace kdeb200 {
+
+namespace {
+
+struct Builder {
+  int d;
+  int64_t N;
+  const double *pts;          // d x N, original order
+  std::vector<int64_t> ord;   // leaf slot -> original index
+  int64_t *left, *right, *lowest, *highest;
+  int64_t next = 2;
+  std::vector<int64_t> post;  // internal nodes in calcStats order
+
+  inline double key(int64_t slot, int dim) const { return pts[ord[slot] * d + dim]; }
+
+  int spread_dim(int64_t lo, int64_t hi) const {  // slots lo..hi-1 (the last leaf is excluded, as in the reference)
+    double best = 0.0;
+    int arg = 0;
+    const double w = 1.0 / (double)(hi - lo);
+    for (int k = 0; k < d; ++k) {
+      double mean = 0.0;
+      for (int64_t s = lo; s < hi; ++s) mean = mean + w * key(s, k);
+      double var = 0.0;
+      for (int64_t s = lo; s < hi; ++s) {
+        const double df = key(s, k) - mean;
+        var += df * df;
+      }
+      if (var > best) {
+        best = var;
+        arg = k;
+      }
+    }
+    return arg;
+  }
+
+  void nth(int dim, int64_t pos, int64_t lo, int64_t hi) {  // the reference's quick-select, swap for swap
+    while (lo < hi) {
+      const int64_t r = (lo + hi) / 2;
+      std::swap(ord[r], ord[lo]);
+      int64_t m = lo;
+      const int64_t l0 = lo, h0 = hi;
+      for (int64_t i = l0; i <= h0; ++i) {
+        // the pivot sits in slot l0 for the whole pass: only slots > l0 are swap targets
+        if (key(i, dim) - key(l0, dim) < 0.0) {
+          ++m;
+          std::swap(ord[m], ord[i]);
+        }
+      }
+      std::swap(ord[lo], ord[m]);
+      if (m <= pos) lo = m + 1;
+      if (m >= pos) hi = m - 1;
+    }
+  }
+
+  // node ids are the reference's 1-based ids; slots are 0-based leaf positions (node = N+1+slot)
+  void topo(int64_t lo, int64_t hi, int64_t root) {
+    const int64_t nlo = N + 1 + lo, nhi = N + 1 + hi;
+    if (lo == hi) {  // single-point tree
+      lowest[root - 1] = nlo;
+      highest[root - 1] = nhi;
+      left[root - 1] = nlo;
+      right[root - 1] = -1;
+      post.push_back(-root);  // negative: "left child counted once" special case
+      return;
+    }
+    const int dim = spread_dim(lo, hi);
+    const int64_t split = (lo + hi) / 2;
+    nth(dim, split, lo, hi);
+    int64_t l, r;
+    if (split <= lo) l = nlo; else l = next++;
+    if (split + 1 >= hi) r = nhi; else r = next++;
+    lowest[root - 1] = nlo;
+    highest[root - 1] = nhi;
+    left[root - 1] = l;
+    right[root - 1] = r;
+    if (l != nlo) topo(lo, split, l);
+    if (r != nhi) topo(split + 1, hi, r);
+    post.push_back(root);
+  }
+};
+
+}  // namespace
+
+int tree_build_host(int d, int64_t N, const double *points, const double *weights, const double *bw_var,
+                    double *centers, double *ranges, double *wout, double *means, double *bandwidth,
+                    int64_t *left, int64_t *right, int64_t *lowest, int64_t *highest, int64_t *perm) {
+  if (d < 1 || N < 1) KDE_FAIL(2, "tree_build: need d >= 1 and N >= 1 (got d=%d N=%lld)", d, (long long)N);
+  const int64_t NN = 2 * N;
+  std::memset(centers, 0, sizeof(double) * NN * d);
+  std::memset(ranges, 0, sizeof(double) * NN * d);
+  std::memset(means, 0, sizeof(double) * NN * d);
+  std::memset(bandwidth, 0, sizeof(double) * NN * d);
+  std::memset(wout, 0, sizeof(double) * NN);
+  for (int64_t i = 0; i < NN; ++i) {
+    left[i] = right[i] = lowest[i] = highest[i] = 1;  // ones(Int, 2Np)
+    perm[i] = 0;
+  }
+  Builder b;
+  b.d = d; b.N = N; b.pts = points;
+  b.left = left; b.right = right; b.lowest = lowest; b.highest = highest;
+  b.ord.resize(N);
+  for (int64_t i = 0; i < N; ++i) b.ord[i] = i;
+  for (int64_t i = N; i < NN; ++i) {  // leaves
+    lowest[i] = highest[i] = left[i] = i + 1;
+    right[i] = -1;
+  }
+  b.post.reserve(N);
+  b.topo(0, N - 1, 1);
+
+  for (int64_t s = 0; s < N; ++s) {  // gather the leaf payload once
+    const int64_t o = b.ord[s], node = N + s;
+    perm[node] = o + 1;
+    wout[node] = weights[o];
+    for (int k = 0; k < d; ++k) {
+      centers[node * d + k] = points[o * d + k];
+      means[node * d + k] = points[o * d + k];
+      bandwidth[node * d + k] = bw_var[k];
+    }
+  }
+  for (int64_t e : b.post) {  // node statistics, children before parents
+    const int64_t root = e < 0 ? -e : e;
+    const int64_t L = left[root - 1];
+    const int64_t R = e < 0 ? L : right[root - 1];  // N == 1: right temporarily aliases left
+    double *c = centers + (root - 1) * d, *rg = ranges + (root - 1) * d;
+    const double *cl = centers + (L - 1) * d, *cr = centers + (R - 1) * d;
+    const double *rl = ranges + (L - 1) * d, *rr = ranges + (R - 1) * d;
+    for (int k = 0; k < d; ++k) {
+      const double hiL = cl[k] + rl[k], hiR = cr[k] + rr[k];
+      const double maxi = hiL > hiR ? hiL : hiR;
+      const double loL = cl[k] - rl[k], loR = cr[k] - rr[k];
+      const double mini = loL < loR ? loL : loR;
+      const double half = (maxi - mini) / 2.0;
+      rg[k] = half;
+      c[k] = mini + half;
+    }
+    wout[root - 1] = (L != R) ? wout[L - 1] + wout[R - 1] : wout[L - 1];
+    double wl = wout[L - 1], wr = wout[R - 1];
+    const double wt = wl + wr + DBL_EPSILON;
+    wl /= wt;
+    wr /= wt;
+    double *m = means + (root - 1) * d, *bwd = bandwidth + (root - 1) * d;
+    const double *ml = means + (L - 1) * d, *mr = means + (R - 1) * d;
+    const double *bl = bandwidth + (L - 1) * d, *br = bandwidth + (R - 1) * d;
+    for (int k = 0; k < d; ++k) {
+      const double mk = wl * ml[k] + wr * mr[k];
+      m[k] = mk;
+      bwd[k] = wl * (bl[k] + ml[k] * ml[k]) + wr * (br[k] + mr[k] * mr[k]) - mk * mk;
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- flatten + upload -------
+static inline int even_up(int x) { return (x + 1) & ~1; }
+
+int tree_create(int d, int64_t N, const double *means, const double *bandwidth, const double *weights,
+                const int64_t *left, const int64_t *right, const int64_t *perm, kdeb200_tree_t *out) {
+  if (int rc = ensure_init()) return rc;
+  if (!out) KDE_FAIL(2, "tree_create: out is NULL");
+  if (d < 1 || d > KDEB200_MAX_DIM) KDE_FAIL(3, "tree_create: d=%d outside 1..%d (no CPU fallback)", d, KDEB200_MAX_DIM);
+  if (N < 1) KDE_FAIL(3, "tree_create: N must be >= 1");
+  if (2 * N >= (int64_t)std::numeric_limits<int32_t>::max()) KDE_FAIL(3, "tree_create: N too large");
+  kdeb200_tree_s *t = new kdeb200_tree_s();
+  t->d = d;
+  t->N = N;
+  t->SA = even_up(d + 1);
+  t->SC = even_up(2 * d + 1);
+  t->SE = even_up(d + 1);
+  const int64_t NN = 2 * N;
+  auto valid = [&](int64_t i) { return 0 < i && i <= NN; };
+
+  // uniform leaf bandwidth is what the typed constructors of the reference always produce
+  for (int k = 0; k < d; ++k) t->hvar[k] = bandwidth[N * d + k];
+  for (int64_t i = N; i < NN; ++i)
+    for (int k = 0; k < d; ++k)
+      if (bandwidth[i * d + k] != t->hvar[k]) {
+        delete t;
+        KDE_FAIL(4, "tree_create: per-point bandwidths (multibandwidth != 0) are not supported");
+      }
+
+  // BFS level lists exactly as levelDown! produces them (left then right, leaves persist)
+  std::vector<std::vector<int64_t>> lists;
+  lists.push_back({1});
+  for (;;) {
+    const std::vector<int64_t> &cur = lists.back();
+    std::vector<int64_t> nxt;
+    nxt.reserve(cur.size() * 2);
+    for (int64_t y : cur) {
+      const int64_t l = left[y - 1], r = right[y - 1];
+      if (valid(l)) nxt.push_back(l);
+      if (valid(r)) nxt.push_back(r);
+    }
+    if (nxt == cur) break;
+    if ((int64_t)nxt.size() > N || lists.size() > 80) {
+      delete t;
+      KDE_FAIL(4, "tree_create: malformed child arrays (level list exceeds N)");
+    }
+    lists.push_back(std::move(nxt));
+  }
+  t->depth = (int)lists.size() - 1;
+  for (int64_t y : lists.back())
+    if (y <= N) {
+      delete t;
+      KDE_FAIL(4, "tree_create: malformed tree (internal node %lld without children)", (long long)y);
+    }
+
+  // lay the records out
+  t->levels.resize(lists.size());
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t o = off; off += (n + 1) & ~(int64_t)1; return o; };
+  for (size_t l = 0; l < lists.size(); ++l) {
+    kdeb200::Level &L = t->levels[l];
+    L.n = (int64_t)lists[l].size();
+    bool all_leaf = true;
+    for (int64_t y : lists[l]) all_leaf = all_leaf && (y > N);
+    L.cls = (all_leaf && l > 0) ? 0 : 1;
+    L.offW = take(L.n);
+    if (L.cls == 0) {
+      L.offA = take(L.n * t->SA);
+    } else {
+      L.offB = take(L.n * t->SC);
+      L.offC = take(L.n * t->SC);
+    }
+  }
+  t->buf_doubles = (size_t)off;
+  std::vector<double> h(off, 0.0);
+  bool degen = false;
+  for (size_t l = 0; l < lists.size(); ++l) {
+    const kdeb200::Level &L = t->levels[l];
+    for (int64_t z = 0; z < L.n; ++z) {
+      const int64_t y = lists[l][z];
+      const double w = weights[y - 1];
+      const double lw = std::log(w);
+      h[L.offW + z] = w;
+      if (!(w >= 0.0) || !std::isfinite(w)) degen = true;
+      if (L.cls == 0) {
+        double *r = &h[L.offA + z * t->SA];
+        for (int k = 0; k < d; ++k) {
+          r[k] = means[(y - 1) * d + k];
+          if (!std::isfinite(r[k])) degen = true;
+        }
+        r[d] = lw;
+      } else {
+        double *rb = &h[L.offB + z * t->SC], *rc = &h[L.offC + z * t->SC];
+        double sl = 0.0;
+        for (int k = 0; k < d; ++k) {
+          const double m = means[(y - 1) * d + k], b = bandwidth[(y - 1) * d + k];
+          if (!std::isfinite(m) || !std::isfinite(b) || !(b > 0.0)) degen = true;
+          rb[k] = rc[k] = m;
+          rb[d + k] = -0.5 / b;
+          rc[d + k] = b;
+          sl += std::log(b);
+        }
+        rb[2 * d] = lw - 0.5 * sl;
+        rc[2 * d] = lw;
+      }
+    }
+  }
+  for (int k = 0; k < d; ++k)
+    if (!(t->hvar[k] > 0.0) || !std::isfinite(t->hvar[k])) degen = true;
+  t->degenerate = degen;
+
+  // leaf-order evaluation records and labels
+  std::vector<double> leaf((size_t)N * t->SE, 0.0);
+  std::vector<int64_t> pr(N), lab(lists.back().size());
+  for (int64_t s = 0; s < N; ++s) {
+    const int64_t node = N + s;
+    for (int k = 0; k < d; ++k) leaf[s * t->SE + k] = means[node * d + k];
+    leaf[s * t->SE + d] = weights[node];
+    pr[s] = perm[node] - 1;
+    if (pr[s] < 0 || pr[s] >= N) {
+      delete t;
+      KDE_FAIL(4, "tree_create: permutation entry out of range at leaf %lld", (long long)s);
+    }
+  }
+  for (size_t z = 0; z < lab.size(); ++z) lab[z] = perm[lists.back()[z] - 1] + 1;
+
+  Context &c = ctx();
+  auto fail = [&](cudaError_t e, const char *what) {
+    set_error("tree_create: %s: %s", what, cudaGetErrorString(e));
+    if (t->d_buf) cudaFree(t->d_buf);
+    if (t->d_labels) cudaFree(t->d_labels);
+    if (t->d_leaf) cudaFree(t->d_leaf);
+    if (t->d_perm) cudaFree(t->d_perm);
+    delete t;
+    return 100 + (int)e;
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc(&t->d_buf, sizeof(double) * h.size())) != cudaSuccess) return fail(e, "cudaMalloc records");
+  if ((e = cudaMalloc(&t->d_labels, sizeof(int64_t) * lab.size())) != cudaSuccess) return fail(e, "cudaMalloc labels");
+  if ((e = cudaMalloc(&t->d_leaf, sizeof(double) * leaf.size())) != cudaSuccess) return fail(e, "cudaMalloc leaves");
+  if ((e = cudaMalloc(&t->d_perm, sizeof(int64_t) * pr.size())) != cudaSuccess) return fail(e, "cudaMalloc perm");
+  if ((e = cudaMemcpyAsync(t->d_buf, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return fail(e, "H2D records");
+  if ((e = cudaMemcpyAsync(t->d_labels, lab.data(), sizeof(int64_t) * lab.size(), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return fail(e, "H2D labels");
+  if ((e = cudaMemcpyAsync(t->d_leaf, leaf.data(), sizeof(double) * leaf.size(), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return fail(e, "H2D leaves");
+  if ((e = cudaMemcpyAsync(t->d_perm, pr.data(), sizeof(int64_t) * pr.size(), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return fail(e, "H2D perm");
+  if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return fail(e, "sync");  // host vectors die here
+  t->device_bytes = sizeof(double) * (h.size() + leaf.size()) + sizeof(int64_t) * (lab.size() + pr.size());
+  *out = t;
+  return 0;
+}
+
+int tree_destroy(kdeb200_tree_t t) {
+  if (!t) return 0;
+  cudaFree(t->d_buf);
+  cudaFree(t->d_labels);
+  cudaFree(t->d_leaf);
+  cudaFree(t->d_perm);
+  delete t;
+  return 0;
+}
+
+}  // namespace kdeb200

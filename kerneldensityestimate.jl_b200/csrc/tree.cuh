@@ -1,0 +1,37 @@
+// tree.cuh -- device-resident BallTreeDensity: level-ordered SoA/AoS records (K3).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "common.cuh"
+
+namespace kdeb200 {
+
+// One BFS level of a tree (the reference's levelList after l levelDown! steps,
+// src/MSGibbs01.jl:500-523).  Offsets are in doubles from kdeb200_tree_s::d_buf.
+struct Level {
+  int64_t n = 0;      // nodes on this level
+  int cls = 1;        // 0: every node is a leaf (uniform bandwidth => hoisted arithmetic), 1: general
+  int64_t offW = 0;   // raw weights, n doubles                         (fallback path only)
+  int64_t offA = -1;  // cls 0: records [m_0..m_{d-1}, ln w]            stride SA
+  int64_t offB = -1;  // cls 1: records [m_k.., -0.5/b_k.., ln w - 0.5 sum ln b_k]   stride SC
+  int64_t offC = -1;  // cls 1: records [m_k.., b_k.., ln w]            stride SC
+};
+
+}  // namespace kdeb200
+
+struct kdeb200_tree_s {
+  int d = 0;
+  int64_t N = 0;
+  bool degenerate = false;  // some bandwidth <= 0 or non-finite value: fast arithmetic not valid
+  double hvar[KDEB200_MAX_DIM] = {0};  // the uniform leaf variances (bandwidthMin/Max[1:d])
+  int SA = 0, SC = 0, SE = 0;          // record strides in doubles (even => 16-byte aligned records)
+  std::vector<kdeb200::Level> levels;  // levels[0] = {root}; levels[l], l = 1..depth
+  int depth = 0;                       // last distinct level (all leaves)
+  double *d_buf = nullptr;             // all level records
+  size_t buf_doubles = 0;
+  int64_t *d_labels = nullptr;  // deepest level, level order: permutation + 1 (src/MSGibbs01.jl:615)
+  double *d_leaf = nullptr;     // leaf order (N+1..2N): [x_0..x_{d-1}, w], stride SE -- evalDirect's order
+  int64_t *d_perm = nullptr;    // leaf order: original 0-based index
+  size_t device_bytes = 0;
+};

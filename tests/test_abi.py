@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/kdeb200.h declares (no compute calls: there is no GPU here), the ctypes table matches
+the header, and host-only entry points (tree build) agree with the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "kdeb200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(kdeb200_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g._load_build().build()
+    from kde_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(built):
+    L = ctypes.CDLL(built.SO_PATH)
+    names = header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_ctypes_table_matches_header(built):
+    assert sorted(built.SIGNATURES) == header_symbols()
+
+
+def test_error_channel_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import kde_b200 as K
+    p = K.kde(np.arange(6.0).reshape(2, 3), [1.0])  # host-only: fine
+    with pytest.raises(K.KDEError):  # no CPU fallback: the device path fails loudly
+        K.evaluateDualTree(p, np.zeros((2, 4)))
+
+
+@pytest.mark.parametrize("d,N", [(1, 1), (1, 2), (1, 4), (2, 3), (3, 100), (4, 257), (2, 1024), (8, 33)])
+def test_host_tree_builder_equals_oracle(built, d, N):
+    import kde_b200 as K
+    from oracle.oracle import OKDE
+    rng = np.random.default_rng(d * 1000 + N)
+    pts = rng.standard_normal((d, N))
+    pts[:, N // 2:] = np.round(pts[:, N // 2:], 1)  # ties
+    bw, w = rng.random(d) + 0.1, rng.random(N) + 0.1
+    a, o = K.kde(pts, bw, w), OKDE.kde_bw(pts, bw, w).arrays()
+    for k in ("centers", "ranges", "weights", "left_child", "right_child", "lowest_leaf", "highest_leaf", "permutation"):
+        assert np.array_equal(getattr(a.bt, k), o[k]), k
+    for k in ("means", "bandwidth", "bandwidthMin", "bandwidthMax"):
+        assert np.array_equal(getattr(a, k), o[k]), k
+    assert np.array_equal(K.getPoints(a), pts)
+    assert np.allclose(K.getBW(a)[:, 0], bw, rtol=1e-15) and np.allclose(K.getWeights(a), w / w.sum(), rtol=1e-14)
+
+
+def test_host_api_mirrors(built):
+    import kde_b200 as K
+    from oracle.oracle import OKDE
+    rng = np.random.default_rng(5)
+    pts = rng.standard_normal((3, 50))
+    p, o = K.kde(pts, [0.2, 0.3, 0.4]), OKDE.kde_bw(pts, [0.2, 0.3, 0.4])
+    m, om = K.marginal(p, [1, 3]), o.marginal([1, 3])
+    assert np.array_equal(m.means, om.arrays()["means"]) and np.array_equal(m.bandwidth, om.arrays()["bandwidth"])
+    assert K.neighborMinMax(p) == pytest.approx(o.neighbor_minmax(), rel=1e-15)
+    s, idx = K.sample(p, 20, rng=np.random.default_rng(1))
+    assert s.shape == (3, 20) and idx.min() >= 1 and idx.max() <= 50
+    with pytest.raises(K.KDEError):
+        K.kde(pts, [0.1, 0.2])
+    with pytest.raises(K.KDEError):
+        K.kde(pts, [0.1], addop=(lambda a, b: a + b,))

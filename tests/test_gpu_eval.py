@@ -1,0 +1,108 @@
+"""-m gpu: K2 parity (evaluation, LOO evaluation, LOO likelihood, LOOCV) through the C-ABI.
+
+FP64 tolerance (BASELINE.json north_star): 1e-12 relative against the oracle."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import kde_b200 as K
+from oracle.oracle import OKDE
+from tests.util import mixture, relerr, silverman
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+FIX = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_fixtures.json")))
+
+
+@pytest.mark.parametrize("d,N,M", [(1, 300, 500), (2, 100, 100), (3, 1000, 777), (4, 513, 64), (5, 200, 129),
+                                   (8, 150, 257), (3, 5000, 3), (1, 1, 10), (2, 7, 1)])
+def test_eval_matches_oracle(d, N, M):
+    rng = np.random.default_rng(100 + d * 7 + N)
+    pts = mixture(rng, d, N)
+    bw = silverman(pts) if N > 2 else np.full(d, 0.5)
+    w = rng.random(N) + 0.05
+    pos = mixture(rng, d, M) * 1.2
+    p = K.kde(pts, bw, w)
+    o = OKDE.kde_bw(pts, bw, w)
+    got = K.evaluateDualTree(p, pos)
+    exp = o.evaluate(pos)
+    assert relerr(got, exp) < TOL
+    assert relerr(p(pos), exp) < TOL  # functor form
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_single_kernel_is_normal_pdf(d):
+    mu = np.arange(1, d + 1, dtype=np.float64).reshape(d, 1)
+    h = np.linspace(0.3, 0.9, d)
+    p = K.kde(mu, h)
+    x = mu + np.linspace(-3, 3, 25)[None, :] * h[:, None]
+    exp = np.prod(np.exp(-0.5 * ((x - mu) / h[:, None]) ** 2) / (np.sqrt(2 * np.pi) * h[:, None]), axis=0)
+    assert relerr(K.evaluateDualTree(p, x), exp) < 1e-13
+
+
+def test_far_tail_and_underflow():
+    p = K.kde(np.array([[0.0, 1.0]]), [0.1])
+    o = OKDE.kde_bw(np.array([[0.0, 1.0]]), [0.1])
+    x = np.array([[3.0, 3.7, 3.8, 5.0, 50.0]])  # exponents -450 ... beyond underflow
+    got, exp = K.evaluateDualTree(p, x), o.evaluate(x)
+    assert np.all((exp == 0) == (got == 0))
+    nz = exp > 1e-290
+    assert relerr(got[nz], exp[nz]) < 1e-11
+
+
+@pytest.mark.parametrize("d,N", [(1, 100), (2, 300), (3, 1000), (1, 2500)])
+def test_loo_eval_and_entropy(d, N):
+    rng = np.random.default_rng(5 + d + N)
+    pts = mixture(rng, d, N)
+    bw = silverman(pts)
+    w = rng.random(N) + 0.1
+    p, o = K.kde(pts, bw, w), OKDE.kde_bw(pts, bw, w)
+    assert relerr(K.evaluateDualTree(p, p), o.evaluate()) < TOL
+    assert relerr(K.evaluateDualTree(p, pts, True), o.evaluate()) < TOL
+    assert abs(K.entropy(p) - o.entropy()) <= TOL * abs(o.entropy())
+    assert abs(K.evalAvgLogL(p, p) + o.entropy()) <= TOL * abs(o.entropy())
+    q, oq = K.kde(pts[:, : N // 2] + 0.1, bw), OKDE.kde_bw(pts[:, : N // 2] + 0.1, bw)
+    assert abs(K.evalAvgLogL(p, q) - o.eval_avg_logl(oq)) <= 1e-11 * abs(o.eval_avg_logl(oq))
+    for a in (0.5, 1.0, 1.7):
+        assert abs(K.nLOO_LL(a, p) - o.nloo_ll(a)) <= TOL * abs(o.entropy())
+
+
+def test_zero_rule_gives_inf():
+    p = K.kde(np.array([[0.0, 1000.0]]), [0.01])
+    assert K.entropy(p) == math.inf and K.evalAvgLogL(p, p) == -math.inf
+
+
+def test_lcv_golden_fixture():
+    """kde!(x) on the reference's 100 fixed points: LOOCV variance 0.00272597 (test/runtests.jl:104-116)."""
+    case = FIX["UnitTest1Dlcv01"]
+    pts = np.array(case["points"])
+    cnt = []
+    p = K.kde(pts)
+    o = OKDE.kde_lcv(pts)
+    assert abs(p.bandwidthMin[0] - case["expected"]["bwMin"][0]) < 5e-9
+    assert abs(p.bandwidthMin[0] - o.arrays()["bandwidthMin"][0]) < 1e-12
+    exp = case["expected"]
+    for mine, name in [(p.bt.centers, "centers"), (p.bt.ranges, "ranges"), (p.means, "means"), (p.bandwidth, "bandwidth")]:
+        assert np.linalg.norm(mine - np.array(exp[name])) <= case["tol"]
+    pp = K.ksize(K.marginal(K.kde(pts, [1.0]), [1]), _count=cnt)
+    assert cnt == [20]
+
+
+def test_lcv_multidim_matches_oracle():
+    rng = np.random.default_rng(9)
+    pts = mixture(rng, 3, 400)
+    p, o = K.kde(pts), OKDE.kde_lcv(pts)
+    assert relerr(p.bandwidthMin[:3], o.arrays()["bandwidthMin"][:3]) < 1e-10
+
+
+def test_errors():
+    p = K.kde(np.zeros((2, 5)) + np.arange(5), [1.0])
+    with pytest.raises(K.KDEError):
+        K.evaluateDualTree(p, np.zeros((3, 4)))
+    with pytest.raises(K.KDEError):
+        K.evaluateDualTree(p, np.zeros((2, 4)), addop=(lambda a, b: a + b,))
+    with pytest.raises(K.KDEError):
+        K.kde(np.zeros((9, 5)) + np.arange(5), [1.0])._dev()

@@ -1,0 +1,165 @@
+"""-m gpu: K1 parity.  Mode (a) of BASELINE.json: identical injected uniform/normal variates =>
+labels identical to the oracle, product points within 1e-10 relative (FP64).  Mode (b): the
+free-running Philox stream is reproduced exactly by injecting kdeb200_philox_streams() into the
+oracle, plus the reference's own statistical bands (test/runtests.jl:167-201)."""
+import numpy as np
+import pytest
+
+import kde_b200 as K
+from oracle import oracle as O
+from tests.util import mixture, silverman
+
+pytestmark = pytest.mark.gpu
+PT_TOL = 1e-10
+
+
+def make(rng, d, N, shift=0.0, bw=None, weights=None):
+    pts = mixture(rng, d, N, shift)
+    if bw is None:
+        bw = silverman(pts) if N > 2 else np.full(d, 0.7)
+    return K.kde(pts, bw, weights), O.OKDE.kde_bw(pts, bw, weights)
+
+
+def compare(ktrees, otrees, Np, T, rng, add_entropy=True, mask=None):
+    nU, nN = O.prod_sizes(otrees, Np, T)
+    U, G = rng.random(nU), rng.standard_normal(nN)
+    epts, eind = O.gibbs(otrees, Np, T, U, G, add_entropy=add_entropy, mask=mask)
+    dummy = K.kde(np.zeros((ktrees[0].bt.dims, Np)) + np.arange(Np), [1.0]) if Np > 0 else None
+    gpts, gind = K.prodAppxMSGibbsS(dummy, ktrees, None, None, Niter=T, randU=U, randN=G, addEntropy=add_entropy,
+                                    partialDimMask=mask)
+    assert gind.shape == eind.shape and gpts.shape == epts.shape
+    nbad = int(np.sum(np.any(gind != eind, axis=0)))
+    assert nbad == 0, "label mismatches in %d of %d samples" % (nbad, Np)
+    scale = np.maximum(np.abs(epts), 1e-3 * np.max(np.abs(epts)) + 1e-300)
+    assert float(np.max(np.abs(gpts - epts) / scale)) < PT_TOL
+    return gpts, gind
+
+
+@pytest.mark.parametrize("d,M,N,Np,T", [
+    (2, 2, 100, 100, 5),      # README product (BASELINE config 1)
+    (3, 6, 100, 100, 5),      # testProds default
+    (2, 4, 100, 100, 5), (4, 6, 100, 200, 10), (3, 5, 300, 100, 5), (2, 7, 100, 300, 5), (3, 2, 100, 100, 100),
+    (1, 2, 64, 150, 3), (3, 3, 33, 130, 5), (5, 3, 50, 64, 2), (8, 2, 40, 64, 2), (1, 3, 2, 50, 5),
+    (2, 3, 1, 40, 3), (3, 1, 50, 40, 3), (2, 16, 20, 33, 1), (3, 2, 100, 1, 5), (2, 2, 100, 100, 0),
+])
+def test_injected_streams_match_oracle(d, M, N, Np, T):
+    rng = np.random.default_rng(1000 * d + 10 * M + N + T)
+    pairs = [make(rng, d, N, 0.25 * j) for j in range(M)]
+    compare([p[0] for p in pairs], [p[1] for p in pairs], Np, T, rng)
+
+
+def test_mixed_sizes_beta_rayleigh_shape():
+    """BASELINE config 2 shape: 1-D, 300 and 100 components (level lists of different depth)."""
+    rng = np.random.default_rng(2)
+    a = rng.beta(1.0, 0.45, size=(1, 300))
+    b = rng.rayleigh(0.5, size=(1, 100)) - 0.5
+    ka, oa = K.kde(a, [0.05]), O.OKDE.kde_bw(a, [0.05])
+    kb, ob = K.kde(b, [0.08]), O.OKDE.kde_bw(b, [0.08])
+    compare([ka, kb], [oa, ob], 2000, 5, rng)
+
+
+def test_large_trees_c4_shape():
+    """BASELINE config 4 shape at a sample count the oracle finishes in seconds."""
+    rng = np.random.default_rng(4)
+    pairs = [make(rng, 3, 4096, 0.25 * j) for j in range(8)]
+    compare([p[0] for p in pairs], [p[1] for p in pairs], 192, 5, rng)
+
+
+def test_weighted_and_lcv_bandwidth():
+    rng = np.random.default_rng(8)
+    pts = [rng.standard_normal((2, 100)) + s for s in (0.0, 2.0)]
+    kt = [K.kde(p) for p in pts]
+    ot = [O.OKDE.kde_lcv(p) for p in pts]
+    compare(kt, ot, 100, 5, rng)
+    w = rng.random(100) + 0.01
+    kt = [K.kde(p, [0.3, 0.4], w) for p in pts]
+    ot = [O.OKDE.kde_bw(p, [0.3, 0.4], w) for p in pts]
+    compare(kt, ot, 100, 5, rng)
+
+
+def test_add_entropy_false_is_precision_weighted_mean():
+    rng = np.random.default_rng(11)
+    pairs = [make(rng, 2, 50, 0.5 * j) for j in range(3)]
+    kt, ot = [p[0] for p in pairs], [p[1] for p in pairs]
+    pts, ind = compare(kt, ot, 64, 5, rng, add_entropy=False)
+    lam = np.stack([1.0 / (K.getBW(t)[:, 0] ** 2) for t in kt])          # M x d
+    for s in range(64):
+        mus = np.stack([K.getPoints(t)[:, ind[j, s] - 2] for j, t in enumerate(kt)])  # label = index + 1
+        exp = (lam * mus).sum(0) / lam.sum(0)
+        assert np.allclose(pts[:, s], exp, rtol=1e-12, atol=1e-14)
+
+
+def test_partial_dim_mask():
+    """test/testPartialProd.jl: masked dims poisoned with 9999999 must not leak."""
+    rng = np.random.default_rng(12)
+    p1, p2, p3 = rng.random((2, 100)) + 10.0, rng.random((2, 100)), rng.random((2, 100)) - 10.0
+    bw = [0.1, 0.1]
+    p1[1, :] = 9999999.0
+    p3[0, :] = 9999999.0
+    mask = [[True, False], [True, True], [False, True]]
+    kt = [K.kde(p, bw) for p in (p1, p2, p3)]
+    ot = [O.OKDE.kde_bw(p, bw) for p in (p1, p2, p3)]
+    pts, _ = compare(kt, ot, 100, 3, rng, mask=mask)
+    assert np.sum((0 < pts[0]) & (pts[0] < 10)) > 80 and np.sum((-10 < pts[1]) & (pts[1] < 0)) > 80
+
+
+def test_two_single_kernels_give_gaussian_product():
+    p1, p2 = K.kde(np.array([[1.0]]), [0.5]), K.kde(np.array([[3.0]]), [1.0])
+    dummy = K.kde(np.zeros((1, 4000)) + np.arange(4000), [1.0])
+    pts, ind = K.prodAppxMSGibbsS(dummy, [p1, p2], None, None, Niter=5, seed=7)
+    v = 1 / (1 / .25 + 1)
+    m = v * (1 / .25 + 3)
+    assert abs(pts.mean() - m) < 0.03 and abs(pts.var() - v) < 0.02 and np.all(ind == 2)
+
+
+def test_philox_mode_is_reproduced_by_injection_and_by_oracle():
+    rng = np.random.default_rng(21)
+    pairs = [make(rng, 3, 200, 0.25 * j) for j in range(4)]
+    kt, ot = [p[0] for p in pairs], [p[1] for p in pairs]
+    Np, T, seed = 300, 5, 20261017
+    L, perU, perN, evals = K.gibbs_sizes(kt, T)
+    assert L == O.gibbs_nlevels(ot) and perU == 4 * (1 + L * (1 + T)) and perN == 3 * (L + 1)
+    dummy = K.kde(np.zeros((3, Np)) + np.arange(Np), [1.0])
+    p0, i0 = K.prodAppxMSGibbsS(dummy, kt, None, None, Niter=T, seed=seed)
+    U, G = K.philox_streams(seed, Np, perU, perN)
+    assert 0.0 <= U.min() and U.max() < 1.0 and abs(U.mean() - 0.5) < 0.01 and abs(G.std() - 1.0) < 0.02
+    p1, i1 = K.prodAppxMSGibbsS(dummy, kt, None, None, Niter=T, randU=U, randN=G)
+    assert np.array_equal(i0, i1) and np.array_equal(p0, p1)
+    ep, ei = O.gibbs(ot, Np, T, U, G)
+    assert np.array_equal(i0, ei) and np.max(np.abs(p0 - ep)) < 1e-10 * np.max(np.abs(ep))
+    # sharding invariance: any split of the sample range gives the same chains
+    a, ai = K.prodAppxMSGibbsS(dummy, kt, None, None, Niter=T, seed=seed, s0=0, s1=77)
+    b, bi = K.prodAppxMSGibbsS(dummy, kt, None, None, Niter=T, seed=seed, s0=77, s1=Np)
+    assert np.array_equal(np.hstack([a, b]), p0) and np.array_equal(np.hstack([ai, bi]), i0)
+    a, ai = K.prodAppxMSGibbsS(dummy, kt, None, None, Niter=T, randU=U, randN=G, s0=130, s1=Np)
+    assert np.array_equal(a, p0[:, 130:]) and np.array_equal(ai, i0[:, 130:])
+
+
+@pytest.mark.parametrize("D,M,N,n,T", [(2, 2, 100, 100, 5), (3, 6, 100, 100, 10), (3, 5, 300, 100, 5)])
+def test_reference_statistical_bands(D, M, N, n, T):
+    """testProds (test/runtests.jl:167-187): |mean| < prodDev, per-dim std in (0.66, 1.33) prodDev."""
+    rng = np.random.default_rng(77 + M)
+    ok = 0
+    for rep in range(4):
+        P = [K.kde(rng.standard_normal((D, N))) for _ in range(M)]
+        dummy = K.kde(rng.standard_normal((D, n)), [1.0])
+        pGM, _ = K.prodAppxMSGibbsS(dummy, P, None, None, Niter=T, seed=rep + 1)
+        prodDev = np.sqrt(1.0 / M)
+        t1 = np.linalg.norm(pGM.mean(axis=1)) < prodDev
+        t2 = np.all((0.66 * prodDev < pGM.std(axis=1, ddof=1)) & (pGM.std(axis=1, ddof=1) < 1.33 * prodDev))
+        ok += int(t1 and t2)
+    assert ok >= 2  # the reference asks for 5 of 10
+
+
+def test_product_operator_and_errors():
+    rng = np.random.default_rng(3)
+    p, q = K.kde(rng.standard_normal((2, 100))), K.kde(2.0 + rng.standard_normal((2, 100)))
+    pq = p * q
+    assert K.Npts(pq) == 100 and K.Ndim(pq) == 2
+    assert np.all(np.abs(K.getPoints(pq).mean(axis=1) - 1.0) < 0.5)
+    with pytest.raises(K.KDEError):
+        K.prodAppxMSGibbsS(p, [p, K.kde(rng.standard_normal((3, 10)), [1.0])], None, None)
+    with pytest.raises(K.KDEError):
+        K.prodAppxMSGibbsS(p, [p, q], None, None, randU=np.zeros(10), randN=np.zeros(10))
+    with pytest.raises(K.KDEError):
+        K.prodAppxMSGibbsS(p, [p, q], None, None, getMu=(lambda *a: 0,))
