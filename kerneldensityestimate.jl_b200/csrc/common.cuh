@@ -88,35 +88,73 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t sample, 
 }
 
 // ---------------------------------------------------------------- FP64 exp --------------
-// exp(x) = 2^(n/64 >> 6) * T[n & 63] * e^r,  n = rint(x*64/ln2), |r| <= ln2/128.
-// 10 FP64-pipe instructions (stock exp(): 14 DFMA + 2 DADD + 1 DMUL) + one shared-memory
-// table load; truncation error r^6/720 <= 3.5e-17, total error ~1 ulp.  |x| > 700 (results
-// near the subnormal / overflow range) takes the libdevice path so denormals match IEEE.
+// exp(x) = 2^(n >> 6) * T[n & 63] * e^r,  n = rint(x*64/ln2), |r| <= ln2/128.
+// 10 FP64-pipe instructions (stock exp(): 14 DFMA + 2 DADD + 1 DMUL) + one shared-memory table
+// load; truncation error r^6/720 <= 3.5e-17, total error ~1 ulp.  The core is branch-free so that
+// independent evaluations interleave in one basic block (the FP64 pipe needs >= 4 independent
+// chains per scheduler); coefficients sit in the constant bank so DFMA reads them as operands.
 #define KDE_EXP_TAB 64
-__device__ __forceinline__ double kde_exp(double x, const double *__restrict__ tab) {
-  const double L2E64 = 92.33248261689366;            // 64/ln2
-  const double C1 = 1.0830424696249145e-02;          // ln2/64 (rounded)
-  const double C2 = 3.623510646634843e-19;           // ln2/64 - C1 (residual, from 60-digit ln2)
-  const double SHIFT = 6755399441055744.0;           // 1.5 * 2^52
+__constant__ double kExpC[8] = {
+    92.33248261689366,       // 64/ln2
+    6755399441055744.0,      // 1.5 * 2^52
+    -1.0830424696249145e-02, // -ln2/64 (rounded)
+    -3.623510646634843e-19,  // -(ln2/64 - rounded), from 60-digit ln2
+    8.3333333333333332e-03,  // 1/120
+    4.1666666666666664e-02,  // 1/24
+    1.6666666666666666e-01,  // 1/6
+    0.5};
+
+// valid for |x| <= 700 (normal results); anything else must be fixed up by the caller
+__device__ __forceinline__ double kde_exp_core(double x, const double *__restrict__ tab) {
+  const double t = __fma_rn(x, kExpC[0], kExpC[1]);
+  const int n = __double2loint(t);
+  const double nf = __dadd_rn(t, -kExpC[1]);
+  double r = __fma_rn(nf, kExpC[2], x);
+  r = __fma_rn(nf, kExpC[3], r);
+  double q = __fma_rn(r, kExpC[4], kExpC[5]);
+  q = __fma_rn(q, r, kExpC[6]);
+  q = __fma_rn(q, r, kExpC[7]);
+  const double r2 = __dmul_rn(r, r);
+  const double p = __fma_rn(q, r2, r);
+  const double T = tab[n & (KDE_EXP_TAB - 1)];
+  const double y = __fma_rn(T, p, T);
+  return __hiloint2double(__double2hiint(y) + (n >> 6) * 1048576, __double2loint(y));
+}
+
+// Gibbs flavour: x < -700 (p < 1e-304) flushes to 0, x > 700 saturates to +inf, negative NaN -> 0
+// (the reference maps NaN weights to 0, src/MSGibbs01.jl:302).  A flushed term can never matter:
+// either pT >= 1e-99 and the term is < 1e-205 of it, or every term is that small and the
+// pT < 1e-99 fallback (:311) fires with or without it.  Integer compares: no FP64-pipe cost.
+__device__ __forceinline__ double kde_exp_flush(double x, const double *__restrict__ tab) {
+  const double y = kde_exp_core(x, tab);
+  const int hx = __double2hiint(x);
+  const bool under = (unsigned)hx > 0xC085E000u;
+  const bool over = hx > 0x4085E000;
+  const int hi = under ? 0 : (over ? 0x7FF00000 : __double2hiint(y));
+  const int lo = (under || over) ? 0 : __double2loint(y);
+  return __hiloint2double(hi, lo);
+}
+
+__device__ __forceinline__ bool kde_exp_out_of_range(double x) {
+  return (unsigned)(__double2hiint(x) & 0x7FFFFFFF) > 0x4085E000u;
+}
+
+// reciprocal / reciprocal square root of a normal, positive double without the libdevice
+// special-case branches: MUFU seed (2^-22) + one cubic step -> < 1 ulp + rounding
+__device__ __forceinline__ double kde_rcp(double c) {
   double y;
-  if (fabs(x) <= 700.0) {
-    const double t = __fma_rn(x, L2E64, SHIFT);
-    const int n = __double2loint(t);
-    const double nf = __dadd_rn(t, -SHIFT);
-    double r = __fma_rn(nf, -C1, x);
-    r = __fma_rn(nf, -C2, r);
-    double q = __fma_rn(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
-    q = __fma_rn(q, r, 1.6666666666666666e-01);
-    q = __fma_rn(q, r, 0.5);
-    const double r2 = __dmul_rn(r, r);
-    const double p = __fma_rn(q, r2, r);
-    const double T = tab[n & (KDE_EXP_TAB - 1)];
-    y = __fma_rn(T, p, T);
-    y = __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
-  } else {
-    y = exp(x);
-  }
-  return y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(c));
+  const double e = __fma_rn(-c, y, 1.0);
+  const double t = __fma_rn(e, e, e);
+  return __fma_rn(y, t, y);
+}
+__device__ __forceinline__ double kde_rsqrt(double c) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(c));
+  const double e = __fma_rn(-c, __dmul_rn(y, y), 1.0);  // 1 - c y^2
+  double u = __fma_rn(e, 0.375, 0.5);
+  u = __dmul_rn(u, e);
+  return __fma_rn(y, u, y);
 }
 
 // ---------------------------------------------------------------- TMA bulk + mbarrier ---

@@ -38,13 +38,35 @@ struct Rec {
   static constexpr int SE = (D + 2) & ~1;
 };
 
+template <int S>
+__device__ __forceinline__ void load_rec(const double *__restrict__ r, double (&rr)[S]) {
+#pragma unroll
+  for (int k = 0; k < S; k += 2) {
+    const double2 v = *reinterpret_cast<const double2 *>(r + k);
+    rr[k] = v.x;
+    rr[k + 1] = v.y;
+  }
+}
+
+// -0.5 * sum_k (x_k - mu_k)^2 / var_k   (distGauss! exponent, src/DualTree01.jl:32-44)
+template <int D, int S>
+__device__ __forceinline__ double quad(const double (&x)[D], const double (&r)[S], const double (&ich)[D]) {
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double df = __dadd_rn(x[k], -r[k]);
+    acc = __fma_rn(__dmul_rn(df, df), ich[k], acc);
+  }
+  return acc;
+}
+
 template <int D, int Q, bool LOO>
 __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant__ EvalParams P) {
   constexpr int SE = Rec<D>::SE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tiles = reinterpret_cast<double *>(smem_raw);
-  double *tab = reinterpret_cast<double *>(smem_raw + EV_STAGES * EV_TILE_BYTES);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + EV_STAGES * EV_TILE_BYTES + KDE_EXP_TAB * 8);
+  __shared__ __align__(16) double tab[KDE_EXP_TAB];
+  __shared__ __align__(8) uint64_t bars[EV_STAGES];
 
   const int tid = threadIdx.x;
   if (tid < KDE_EXP_TAB) tab[tid] = P.exptab[tid];
@@ -100,40 +122,52 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
     const double *rec = tiles + (size_t)(t % EV_STAGES) * (EV_TILE_BYTES / 8);
     const bool check = LOO && (a < qhi) && (a + cnt > qlo);
     if (!check) {
-#pragma unroll 2
-      for (int c = 0; c < cnt; ++c) {
-        const double *r = rec + c * SE;
-        double rr[SE];
+      int c = 0;
+      for (; c + 2 <= cnt; c += 2) {  // 2 records x Q queries = independent exp chains in one basic block
+        double ra[SE], rb[SE], e[2][Q], a[2][Q];
+        load_rec<SE>(rec + c * SE, ra);
+        load_rec<SE>(rec + (c + 1) * SE, rb);
+        bool bad = false;
 #pragma unroll
-        for (int k = 0; k < SE; k += 2) {
-          const double2 v = *reinterpret_cast<const double2 *>(r + k);
-          rr[k] = v.x;
-          rr[k + 1] = v.y;
+        for (int i = 0; i < Q; ++i) {
+          a[0][i] = quad<D>(x[i], ra, ich);
+          a[1][i] = quad<D>(x[i], rb, ich);
+          e[0][i] = kde_exp_core(a[0][i], tab);
+          e[1][i] = kde_exp_core(a[1][i], tab);
+          bad = bad || kde_exp_out_of_range(a[0][i]) || kde_exp_out_of_range(a[1][i]);
+        }
+        if (bad) {  // far tails: results near the subnormal range take the IEEE-exact libdevice path
+#pragma unroll
+          for (int i = 0; i < Q; ++i) {
+            e[0][i] = exp(a[0][i]);
+            e[1][i] = exp(a[1][i]);
+          }
         }
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
-          double acc = 0.0;
+          sum[i] = __fma_rn(e[0][i], ra[D], sum[i]);
+          sum[i] = __fma_rn(e[1][i], rb[D], sum[i]);
+        }
+      }
+      for (; c < cnt; ++c) {
+        double ra[SE];
+        load_rec<SE>(rec + c * SE, ra);
 #pragma unroll
-          for (int k = 0; k < D; ++k) {
-            const double df = __dadd_rn(x[i][k], -rr[k]);
-            acc = __fma_rn(__dmul_rn(df, df), ich[k], acc);
-          }
-          sum[i] = __fma_rn(kde_exp(acc, tab), rr[D], sum[i]);
+        for (int i = 0; i < Q; ++i) {
+          const double a = quad<D>(x[i], ra, ich);
+          const double e = kde_exp_out_of_range(a) ? exp(a) : kde_exp_core(a, tab);
+          sum[i] = __fma_rn(e, ra[D], sum[i]);
         }
       }
     } else {
       for (int c = 0; c < cnt; ++c) {
-        const double *r = rec + c * SE;
+        double ra[SE];
+        load_rec<SE>(rec + c * SE, ra);
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int k = 0; k < D; ++k) {
-            const double df = __dadd_rn(x[i][k], -r[k]);
-            acc = __fma_rn(__dmul_rn(df, df), ich[k], acc);
-          }
-          const double e = kde_exp(acc, tab);
-          if (a + c != self[i]) sum[i] = __fma_rn(e, r[D], sum[i]);  // leave-one-out (src/DualTree01.jl:146)
+          const double a2 = quad<D>(x[i], ra, ich);
+          const double e = kde_exp_out_of_range(a2) ? exp(a2) : kde_exp_core(a2, tab);
+          if (a + c != self[i]) sum[i] = __fma_rn(e, ra[D], sum[i]);  // leave-one-out (src/DualTree01.jl:146)
         }
       }
     }
@@ -272,7 +306,7 @@ int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int6
   double *d_partial = nullptr;
   if (S > 1) KDE_CUDA(cudaMallocAsync(&d_partial, sizeof(double) * S * M, st));
   P.partial = d_partial;
-  const size_t smem = EV_STAGES * EV_TILE_BYTES + KDE_EXP_TAB * 8 + EV_STAGES * 8;
+  const size_t smem = EV_STAGES * EV_TILE_BYTES;
   dim3 grid((unsigned)nqb, (unsigned)S);
   cudaError_t e = loo ? launch_eval<true>(d, P, grid, smem, st) : launch_eval<false>(d, P, grid, smem, st);
   if (e != cudaSuccess) KDE_FAIL(100 + (int)e, "eval kernel launch: %s", cudaGetErrorString(e));

@@ -85,46 +85,66 @@ struct Hoist {
   bool act[D];     // dimension participates (partialDimMask logic, :270-285)
 };
 
+// record -> registers with 16-byte loads (records are 16-byte aligned, strides are even)
+template <int S>
+__device__ __forceinline__ void load_rec(const double *__restrict__ r, double (&rr)[S]) {
+#pragma unroll
+  for (int k = 0; k < S; k += 2) {
+    const double2 v = *reinterpret_cast<const double2 *>(r + k);
+    rr[k] = v.x;
+    rr[k + 1] = v.y;
+  }
+}
+
 template <int D, bool MASK>
 __device__ __forceinline__ double eval_A(const double *__restrict__ r, const Hoist<D, MASK> &h,
                                          const double *__restrict__ tab) {
-  double acc = r[D];
+  constexpr int S = (D + 2) & ~1;
+  double rr[S];
+  load_rec<S>(r, rr);
+  double acc = rr[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     if (MASK && !h.act[k]) continue;
-    const double df = __dadd_rn(r[k], -h.mu[k]);
+    const double df = __dadd_rn(rr[k], -h.mu[k]);
     acc = __fma_rn(__dmul_rn(df, df), h.ich[k], acc);
   }
-  return kde_exp(acc, tab);
+  return kde_exp_flush(acc, tab);
 }
 
 template <int D, bool MASK>
 __device__ __forceinline__ double eval_B(const double *__restrict__ r, const Hoist<D, MASK> &h,
                                          const double *__restrict__ tab) {
-  double acc = r[2 * D];
+  constexpr int S = (2 * D + 2) & ~1;
+  double rr[S];
+  load_rec<S>(r, rr);
+  double acc = rr[2 * D];
 #pragma unroll
   for (int k = 0; k < D; ++k) {
-    const double df = __dadd_rn(r[k], -h.mu[k]);
-    acc = __fma_rn(__dmul_rn(df, df), r[D + k], acc);
+    const double df = __dadd_rn(rr[k], -h.mu[k]);
+    acc = __fma_rn(__dmul_rn(df, df), rr[D + k], acc);
   }
-  return kde_exp(acc, tab);
+  return kde_exp_flush(acc, tab);
 }
 
 template <int D, bool MASK>
 __device__ __forceinline__ double eval_C(const double *__restrict__ r, const Hoist<D, MASK> &h,
                                          const double *__restrict__ tab) {
-  double acc = r[2 * D];
+  constexpr int S = (2 * D + 2) & ~1;
+  double rr[S];
+  load_rec<S>(r, rr);
+  double quad = 0.0;
   double prod = 1.0;
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     if (MASK && !h.act[k]) continue;
-    const double c = __dadd_rn(r[D + k], h.cadd[k]);
-    const double df = __dadd_rn(r[k], -h.mu[k]);
-    const double q = __dmul_rn(__dmul_rn(df, df), -0.5);
-    acc = __fma_rn(q, __drcp_rn(c), acc);
+    const double c = __dadd_rn(rr[D + k], h.cadd[k]);
+    const double df = __dadd_rn(rr[k], -h.mu[k]);
+    quad = __fma_rn(__dmul_rn(df, df), kde_rcp(c), quad);
     prod = __dmul_rn(prod, c);
   }
-  return __dmul_rn(kde_exp(acc, tab), rsqrt(prod));
+  const double arg = __fma_rn(quad, -0.5, rr[2 * D]);
+  return __dmul_rn(kde_exp_flush(arg, tab), kde_rsqrt(prod));
 }
 
 template <int D, bool MASK, int VAR>
@@ -167,16 +187,26 @@ __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h,
       const int m = (cnt - z0 < step) ? (cnt - z0) : step;
       const double *r = rec + (size_t)z0 * stride;
       int z = 0;
-      for (; z + 4 <= m; z += 4) {
-        const double p0 = eval_node<D, MASK, VAR>(r, h, tab);
-        const double p1 = eval_node<D, MASK, VAR>(r + stride, h, tab);
-        const double p2 = eval_node<D, MASK, VAR>(r + 2 * stride, h, tab);
-        const double p3 = eval_node<D, MASK, VAR>(r + 3 * stride, h, tab);
-        S = __dadd_rn(S, p0);
-        S = __dadd_rn(S, p1);
-        S = __dadd_rn(S, p2);
-        S = __dadd_rn(S, p3);
-        r += 4 * stride;
+      if (D <= 4) {  // 4 independent evaluation chains per thread; fewer at high d (ptxas 12.9 segfaults otherwise)
+        for (; z + 4 <= m; z += 4) {
+          const double p0 = eval_node<D, MASK, VAR>(r, h, tab);
+          const double p1 = eval_node<D, MASK, VAR>(r + stride, h, tab);
+          const double p2 = eval_node<D, MASK, VAR>(r + 2 * stride, h, tab);
+          const double p3 = eval_node<D, MASK, VAR>(r + 3 * stride, h, tab);
+          S = __dadd_rn(S, p0);
+          S = __dadd_rn(S, p1);
+          S = __dadd_rn(S, p2);
+          S = __dadd_rn(S, p3);
+          r += 4 * stride;
+        }
+      } else if (D <= 6) {
+        for (; z + 2 <= m; z += 2) {
+          const double p0 = eval_node<D, MASK, VAR>(r, h, tab);
+          const double p1 = eval_node<D, MASK, VAR>(r + stride, h, tab);
+          S = __dadd_rn(S, p0);
+          S = __dadd_rn(S, p1);
+          r += 2 * stride;
+        }
       }
       for (; z < m; ++z) {
         S = __dadd_rn(S, eval_node<D, MASK, VAR>(r, h, tab));
@@ -216,8 +246,8 @@ template <int D, bool MASK>
 __global__ void __launch_bounds__(GB_THREADS, 4) gibbs_kernel(const __grid_constant__ GibbsParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tiles = reinterpret_cast<double *>(smem_raw);
-  double *tab = reinterpret_cast<double *>(smem_raw + GB_STAGES * GB_TILE_BYTES);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + GB_STAGES * GB_TILE_BYTES + KDE_EXP_TAB * 8);
+  __shared__ __align__(16) double tab[KDE_EXP_TAB];
+  __shared__ __align__(8) uint64_t bars[GB_STAGES];
   const int tid = threadIdx.x;
   const int M = P.M;
 
@@ -332,7 +362,7 @@ __global__ void __launch_bounds__(GB_THREADS, 4) gibbs_kernel(const __grid_const
           h.ich[k] = -0.5 / c;
           if (!MASK || h.act[k]) prod *= c;
         }
-        scale = rsqrt(prod);
+        scale = kde_rsqrt(prod);
       }
 
       double pT;
@@ -623,7 +653,7 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
     P.labels[j] = t->d_labels;
     for (int k = 0; k < d; ++k) P.hvar[j][k] = t->hvar[k];
   }
-  const size_t smem = GB_STAGES * GB_TILE_BYTES + KDE_EXP_TAB * 8 + GB_STAGES * 8;
+  const size_t smem = GB_STAGES * GB_TILE_BYTES;
   cudaError_t e = cudaErrorInvalidValue;
   switch (d) {
     case 1: e = launch_gibbs_d<1>(P, masked, P.nbatches, smem, st, c.sm_count); break;
