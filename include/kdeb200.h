@@ -121,6 +121,9 @@ int kdeb200_loo_partial(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int
  * FFMA and MUFU.EX2 loops over the whole chip.  which: 0 = DFMA, 1 = FFMA, 2 = MUFU.EX2.
  * Returns achieved instructions/s (per thread-lane) and the elapsed ms. */
 int kdeb200_pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms);
+/* DFMA latency / throughput probe: `ilp` independent dependent chains per thread (1,2,4,8,16) at
+ * a chosen occupancy; used to size the kernels' ILP x warps product. */
+int kdeb200_dfma_probe(int ilp, int blocks_per_sm, int threads, int iters, double *lane_ops_per_s);
 /* Milliseconds spent in the kernels of the last call on this thread (CUDA events). */
 int kdeb200_last_kernel_ms(double *ms, int *launches);
 

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libkdeb200.so")
+SO_PATH = os.environ.get("KDEB200_SO") or os.path.join(_HERE, "libkdeb200.so")
 
 f64p = C.POINTER(C.c_double)
 i64p = C.POINTER(C.c_int64)
@@ -38,6 +38,7 @@ SIGNATURES = {
     "kdeb200_loo_entropy": (C.c_int, [tree_t, f64p, f64p]),
     "kdeb200_loo_partial": (C.c_int, [tree_t, f64p, C.c_int64, C.c_int64, f64p, C.POINTER(C.c_int)]),
     "kdeb200_pipe_peak": (C.c_int, [C.c_int, C.c_int, f64p, f64p]),
+    "kdeb200_dfma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, f64p]),
     "kdeb200_last_kernel_ms": (C.c_int, [f64p, C.POINTER(C.c_int)]),
 }
 

@@ -20,6 +20,35 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(tag, defines):
+    """Experimental builds (tuning sweeps): libkdeb200_<tag>.so with extra -D flags; selected at run
+    time with KDEB200_SO=<path>."""
+    out = os.path.join(HERE, "libkdeb200_%s.so" % tag)
+    bdir = os.path.join(HERE, "build", tag)
+    os.makedirs(bdir, exist_ok=True)
+    procs, objs = [], []
+    build()
+    for s in SOURCES:
+        if s != "gibbs.cu":  # the tuning knobs only touch the Gibbs kernel
+            objs.append(os.path.join(HERE, "build", s.replace(".cu", ".o")))
+            continue
+        o = os.path.join(bdir, s.replace(".cu", ".o"))
+        objs.append(o)
+        cmd = [NVCC] + FLAGS + ["-D%s" % d for d in defines] + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for s, p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(o)
+            raise RuntimeError("nvcc failed on %s (%s)" % (s, tag))
+        lines = o.splitlines()
+        for i, line in enumerate(lines):
+            if "Function properties" in line and "gibbs_kernelILi3ELb0" in line:
+                print(tag, " ".join(x.strip() for x in lines[i + 1:i + 3]))
+    subprocess.check_call([NVCC, "-shared", "-o", out] + objs + ["-ccbin", "/usr/bin/g++"])
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not _stale():
         return OUT

@@ -29,6 +29,7 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
 int philox_streams_device(uint64_t seed, int64_t Np, int64_t perU, int64_t perN, double *d_U, double *d_G,
                           cudaStream_t st);
 int pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms_out);
+int dfma_probe(int ilp, int blocks_per_sm, int threads, int iters, double *lane_ops_per_s);
 
 // RAII device buffer on a stream
 struct DevBuf {
@@ -255,6 +256,10 @@ int kdeb200_loo_entropy(kdeb200_tree_t bd, const double *bw_var, double *H_out) 
 
 int kdeb200_pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms) {
   return pipe_peak(which, iters, lane_ops_per_s, ms);
+}
+
+int kdeb200_dfma_probe(int ilp, int blocks_per_sm, int threads, int iters, double *lane_ops_per_s) {
+  return dfma_probe(ilp, blocks_per_sm, threads, iters, lane_ops_per_s);
 }
 
 }  // extern "C"

@@ -118,14 +118,15 @@ __device__ __forceinline__ double kde_exp_core(double x, const double *__restric
   const double p = __fma_rn(q, r2, r);
   const double T = tab[n & (KDE_EXP_TAB - 1)];
   const double y = __fma_rn(T, p, T);
-  return __hiloint2double(__double2hiint(y) + (n >> 6) * 1048576, __double2loint(y));
+  return __hiloint2double(__double2hiint(y) + (n & ~(KDE_EXP_TAB - 1)) * 16384, __double2loint(y));  // + (n>>6)<<20
 }
 
-// Gibbs flavour: x < -700 (p < 1e-304) flushes to 0, x > 700 saturates to +inf, negative NaN -> 0
+// Gibbs flavour: x < -700 (p < 1e-304) is clamped (or flushed to 0 with KDE_FLUSH_SELECT), negative NaN -> tiny
 // (the reference maps NaN weights to 0, src/MSGibbs01.jl:302).  A flushed term can never matter:
 // either pT >= 1e-99 and the term is < 1e-205 of it, or every term is that small and the
 // pT < 1e-99 fallback (:311) fires with or without it.  Integer compares: no FP64-pipe cost.
 __device__ __forceinline__ double kde_exp_flush(double x, const double *__restrict__ tab) {
+#ifdef KDE_FLUSH_SELECT
   const double y = kde_exp_core(x, tab);
   const int hx = __double2hiint(x);
   const bool under = (unsigned)hx > 0xC085E000u;
@@ -133,6 +134,13 @@ __device__ __forceinline__ double kde_exp_flush(double x, const double *__restri
   const int hi = under ? 0 : (over ? 0x7FF00000 : __double2hiint(y));
   const int lo = (under || over) ? 0 : __double2loint(y);
   return __hiloint2double(hi, lo);
+#else
+  // one integer op: clamp the high word so that x >= -700 (terms below e^-700 ~ 1e-304 are
+  // replaced by ~1e-304, which is equally irrelevant -- see above); x <= 700 is the caller's
+  // contract (exponents are ln w plus non-positive terms, plus at most -0.5 sum ln b_k).
+  const unsigned hx = min((unsigned)__double2hiint(x), 0xC085E000u);
+  return kde_exp_core(__hiloint2double((int)hx, __double2loint(x)), tab);
+#endif
 }
 
 __device__ __forceinline__ bool kde_exp_out_of_range(double x) {

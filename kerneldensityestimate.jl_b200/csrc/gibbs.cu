@@ -29,6 +29,15 @@ constexpr int GB_THREADS = 128;
 constexpr int GB_STAGES = 3;
 constexpr int GB_TILE_BYTES = 8192;
 constexpr int GB_MAXCK = 64;  // checkpoints per draw
+#ifndef GB_UNROLL_A
+#define GB_UNROLL_A 4
+#endif
+#ifndef GB_UNROLL_C
+#define GB_UNROLL_C 2
+#endif
+#ifndef GB_MINBLOCKS
+#define GB_MINBLOCKS 4
+#endif
 
 enum : int { VAR_A = 0, VAR_B = 1, VAR_C = 2 };
 
@@ -96,9 +105,12 @@ __device__ __forceinline__ void load_rec(const double *__restrict__ r, double (&
   }
 }
 
+// One evaluation is split in two stages so that pass 1 can software-pipeline them (stage 1 of
+// node group g overlaps the exp chains of group g-1 in one basic block):
+//   pre_*: record -> exponent argument (and, variant C, the normaliser rsqrt(prod c_k))
+//   fin  : p = exp(arg) [* scale]
 template <int D, bool MASK>
-__device__ __forceinline__ double eval_A(const double *__restrict__ r, const Hoist<D, MASK> &h,
-                                         const double *__restrict__ tab) {
+__device__ __forceinline__ void pre_A(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg, double &sc) {
   constexpr int S = (D + 2) & ~1;
   double rr[S];
   load_rec<S>(r, rr);
@@ -109,12 +121,12 @@ __device__ __forceinline__ double eval_A(const double *__restrict__ r, const Hoi
     const double df = __dadd_rn(rr[k], -h.mu[k]);
     acc = __fma_rn(__dmul_rn(df, df), h.ich[k], acc);
   }
-  return kde_exp_flush(acc, tab);
+  arg = acc;
+  sc = 1.0;
 }
 
 template <int D, bool MASK>
-__device__ __forceinline__ double eval_B(const double *__restrict__ r, const Hoist<D, MASK> &h,
-                                         const double *__restrict__ tab) {
+__device__ __forceinline__ void pre_B(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg, double &sc) {
   constexpr int S = (2 * D + 2) & ~1;
   double rr[S];
   load_rec<S>(r, rr);
@@ -124,15 +136,31 @@ __device__ __forceinline__ double eval_B(const double *__restrict__ r, const Hoi
     const double df = __dadd_rn(rr[k], -h.mu[k]);
     acc = __fma_rn(__dmul_rn(df, df), rr[D + k], acc);
   }
-  return kde_exp_flush(acc, tab);
+  arg = acc;
+  sc = 1.0;
 }
 
 template <int D, bool MASK>
-__device__ __forceinline__ double eval_C(const double *__restrict__ r, const Hoist<D, MASK> &h,
-                                         const double *__restrict__ tab) {
+__device__ __forceinline__ void pre_C(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg, double &sc) {
   constexpr int S = (2 * D + 2) & ~1;
   double rr[S];
   load_rec<S>(r, rr);
+  if (D == 3 && !MASK) {
+    // one MUFU.RSQ64H for the normaliser AND the three reciprocals:
+    //   rs = rsqrt(c0 c1 c2), R = rs^2 = 1/(c0 c1 c2), 1/c_k = R * prod_{i != k} c_i   (38 FP64 instr / node)
+    const double c0 = __dadd_rn(rr[3], h.cadd[0]), c1 = __dadd_rn(rr[4], h.cadd[1]), c2 = __dadd_rn(rr[5], h.cadd[2]);
+    const double d0 = __dadd_rn(rr[0], -h.mu[0]), d1 = __dadd_rn(rr[1], -h.mu[1]), d2 = __dadd_rn(rr[2], -h.mu[2]);
+    const double c01 = __dmul_rn(c0, c1);
+    const double rs = kde_rsqrt(__dmul_rn(c01, c2));
+    const double Rv = __dmul_rn(rs, rs);
+    const double t = __dmul_rn(c2, Rv);
+    double quad = __dmul_rn(__dmul_rn(d2, d2), __dmul_rn(c01, Rv));
+    quad = __fma_rn(__dmul_rn(d0, d0), __dmul_rn(c1, t), quad);
+    quad = __fma_rn(__dmul_rn(d1, d1), __dmul_rn(c0, t), quad);
+    arg = __fma_rn(quad, -0.5, rr[6]);
+    sc = rs;
+    return;
+  }
   double quad = 0.0;
   double prod = 1.0;
 #pragma unroll
@@ -143,16 +171,30 @@ __device__ __forceinline__ double eval_C(const double *__restrict__ r, const Hoi
     quad = __fma_rn(__dmul_rn(df, df), kde_rcp(c), quad);
     prod = __dmul_rn(prod, c);
   }
-  const double arg = __fma_rn(quad, -0.5, rr[2 * D]);
-  return __dmul_rn(kde_exp_flush(arg, tab), kde_rsqrt(prod));
+  arg = __fma_rn(quad, -0.5, rr[2 * D]);
+  sc = kde_rsqrt(prod);
+}
+
+template <int D, bool MASK, int VAR>
+__device__ __forceinline__ void pre_node(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg,
+                                         double &sc) {
+  if (VAR == VAR_A) pre_A<D, MASK>(r, h, arg, sc);
+  else if (VAR == VAR_B) pre_B<D, MASK>(r, h, arg, sc);
+  else pre_C<D, MASK>(r, h, arg, sc);
+}
+
+template <int VAR>
+__device__ __forceinline__ double fin_node(double arg, double sc, const double *__restrict__ tab) {
+  const double e = kde_exp_flush(arg, tab);
+  return (VAR == VAR_C) ? __dmul_rn(e, sc) : e;
 }
 
 template <int D, bool MASK, int VAR>
 __device__ __forceinline__ double eval_node(const double *__restrict__ r, const Hoist<D, MASK> &h,
                                             const double *__restrict__ tab) {
-  if (VAR == VAR_A) return eval_A<D, MASK>(r, h, tab);
-  if (VAR == VAR_B) return eval_B<D, MASK>(r, h, tab);
-  return eval_C<D, MASK>(r, h, tab);
+  double arg, sc;
+  pre_node<D, MASK, VAR>(r, h, arg, sc);
+  return fin_node<VAR>(arg, sc, tab);
 }
 
 // pass 1 over the tiles of one draw: sequential sum, checkpoints every G nodes
@@ -174,50 +216,74 @@ __device__ __forceinline__ void ring_issue(const Ring &R, int64_t q) {
 template <int D, bool MASK, int VAR>
 __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h, const double *__restrict__ tab,
                                         const Ring &R, int64_t &q, double *__restrict__ ck) {
-  const int stride = dr.stride;
-  const int step = dr.G < dr.tnodes ? dr.G : dr.tnodes;
+  // UNR nodes per group; group g's stage 1 is issued together with group g-1's exp chains.
+  // Fewer at high d, where ptxas 12.9 segfaults on wide unrolls.
+  constexpr int UNR = (D <= 4) ? ((VAR == VAR_C) ? GB_UNROLL_C : GB_UNROLL_A) : (D <= 6 ? 2 : 1);
+  constexpr int stride = (VAR == VAR_A) ? ((D + 2) & ~1) : ((2 * D + 2) & ~1);  // == dr.stride
+  const int n = dr.n, G = dr.G;
   double S = 0.0;
   int c = 0;
   int done = 0;
-  for (int t = 0; t < dr.ntiles; ++t, ++q) {
-    const int cnt = (dr.n - done < dr.tnodes) ? (dr.n - done) : dr.tnodes;
-    mbar_wait(&R.bars[q % GB_STAGES], (uint32_t)((q / GB_STAGES) & 1));
-    const double *rec = R.tiles + (size_t)(q % GB_STAGES) * (GB_TILE_BYTES / 8);
-    for (int z0 = 0; z0 < cnt; z0 += step) {
-      const int m = (cnt - z0 < step) ? (cnt - z0) : step;
-      const double *r = rec + (size_t)z0 * stride;
-      int z = 0;
-      if (D <= 4) {  // 4 independent evaluation chains per thread; fewer at high d (ptxas 12.9 segfaults otherwise)
-        for (; z + 4 <= m; z += 4) {
-          const double p0 = eval_node<D, MASK, VAR>(r, h, tab);
-          const double p1 = eval_node<D, MASK, VAR>(r + stride, h, tab);
-          const double p2 = eval_node<D, MASK, VAR>(r + 2 * stride, h, tab);
-          const double p3 = eval_node<D, MASK, VAR>(r + 3 * stride, h, tab);
-          S = __dadd_rn(S, p0);
-          S = __dadd_rn(S, p1);
-          S = __dadd_rn(S, p2);
-          S = __dadd_rn(S, p3);
-          r += 4 * stride;
-        }
-      } else if (D <= 6) {
-        for (; z + 2 <= m; z += 2) {
-          const double p0 = eval_node<D, MASK, VAR>(r, h, tab);
-          const double p1 = eval_node<D, MASK, VAR>(r + stride, h, tab);
-          S = __dadd_rn(S, p0);
-          S = __dadd_rn(S, p1);
-          r += 2 * stride;
-        }
-      }
-      for (; z < m; ++z) {
+  if (G < UNR) {  // tiny levels (n <= 64 * UNR / 2): one node at a time, a checkpoint per G nodes
+    for (int t = 0; t < dr.ntiles; ++t, ++q) {
+      const int cnt = (n - done < dr.tnodes) ? (n - done) : dr.tnodes;
+      mbar_wait(&R.bars[q % GB_STAGES], (uint32_t)((q / GB_STAGES) & 1));
+      const double *r = R.tiles + (size_t)(q % GB_STAGES) * (GB_TILE_BYTES / 8);
+      for (int z = 0; z < cnt; ++z) {
         S = __dadd_rn(S, eval_node<D, MASK, VAR>(r, h, tab));
         r += stride;
+        const int upto = done + z + 1;
+        if ((upto & (G - 1)) == 0 || upto == n) ck[c++] = S;
       }
-      const int upto = done + z0 + m;  // nodes consumed so far
-      if ((upto & (dr.G - 1)) == 0 || upto == dr.n) ck[c++] = S;
+      done += cnt;
+      __syncthreads();
+      if (threadIdx.x == 0 && q + GB_STAGES < R.total) ring_issue(R, q + GB_STAGES);
+    }
+    return S;
+  }
+  double arg[UNR], sc[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    arg[u] = 0.0;
+    sc[u] = 0.0;
+  }
+  int pvalid = 0;  // nodes in the pending group
+  int consumed = 0;
+  for (int t = 0; t < dr.ntiles; ++t, ++q) {
+    const int cnt = (n - done < dr.tnodes) ? (n - done) : dr.tnodes;
+    mbar_wait(&R.bars[q % GB_STAGES], (uint32_t)((q / GB_STAGES) & 1));
+    const double *rec = R.tiles + (size_t)(q % GB_STAGES) * (GB_TILE_BYTES / 8);
+    for (int z0 = 0; z0 < cnt; z0 += UNR) {
+      double narg[UNR], nsc[UNR], p[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)  // a partial last group reads stale (in-bounds) ring data; its p is dropped
+        pre_node<D, MASK, VAR>(rec + (size_t)(z0 + u) * stride, h, narg[u], nsc[u]);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) p[u] = fin_node<VAR>(arg[u], sc[u], tab);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        if (u < pvalid) S = __dadd_rn(S, p[u]);
+      consumed += pvalid;
+      if (pvalid > 0 && (consumed & (G - 1)) == 0) ck[c++] = S;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        arg[u] = narg[u];
+        sc[u] = nsc[u];
+      }
+      pvalid = (cnt - z0 < UNR) ? (cnt - z0) : UNR;
     }
     done += cnt;
-    __syncthreads();  // stage free again
+    __syncthreads();  // stage free again (the pending group lives in registers)
     if (threadIdx.x == 0 && q + GB_STAGES < R.total) ring_issue(R, q + GB_STAGES);
+  }
+  {  // drain the last group
+    double p[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) p[u] = fin_node<VAR>(arg[u], sc[u], tab);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (u < pvalid) S = __dadd_rn(S, p[u]);
+    ck[c++] = S;  // consumed == n
   }
   return S;
 }
@@ -226,9 +292,10 @@ __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h,
 template <int D, bool MASK, int VAR>
 __device__ __forceinline__ int pass2(const Draw &dr, const Hoist<D, MASK> &h, const double *__restrict__ tab, int cs,
                                   double S, double target) {
+  constexpr int stride = (VAR == VAR_A) ? ((D + 2) & ~1) : ((2 * D + 2) & ~1);  // == dr.stride
   const int z0 = cs * dr.G;
   const int z1 = (z0 + dr.G < dr.n) ? z0 + dr.G : dr.n;
-  const double *r = dr.rec + (size_t)z0 * dr.stride;
+  const double *r = dr.rec + (size_t)z0 * stride;
   int zs = z1 - 1;
   bool found = false;
   for (int z = z0; z < z1; ++z) {
@@ -237,13 +304,13 @@ __device__ __forceinline__ int pass2(const Draw &dr, const Hoist<D, MASK> &h, co
       zs = z;
       found = true;
     }
-    r += dr.stride;
+    r += stride;
   }
   return zs;
 }
 
 template <int D, bool MASK>
-__global__ void __launch_bounds__(GB_THREADS, 4) gibbs_kernel(const __grid_constant__ GibbsParams P) {
+__global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const __grid_constant__ GibbsParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tiles = reinterpret_cast<double *>(smem_raw);
   __shared__ __align__(16) double tab[KDE_EXP_TAB];
@@ -549,6 +616,8 @@ static cudaError_t launch_gibbs_d(const GibbsParams &P, bool masked, int grid_ca
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GB_THREADS, smem);
     if (e != cudaSuccess) return e;
@@ -656,6 +725,9 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
   const size_t smem = GB_STAGES * GB_TILE_BYTES;
   cudaError_t e = cudaErrorInvalidValue;
   switch (d) {
+#ifdef GB_ONLY_D3  // tuning builds: one instantiation
+    case 3: e = launch_gibbs_d<3>(P, masked, P.nbatches, smem, st, c.sm_count); break;
+#else
     case 1: e = launch_gibbs_d<1>(P, masked, P.nbatches, smem, st, c.sm_count); break;
     case 2: e = launch_gibbs_d<2>(P, masked, P.nbatches, smem, st, c.sm_count); break;
     case 3: e = launch_gibbs_d<3>(P, masked, P.nbatches, smem, st, c.sm_count); break;
@@ -664,6 +736,7 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
     case 6: e = launch_gibbs_d<6>(P, masked, P.nbatches, smem, st, c.sm_count); break;
     case 7: e = launch_gibbs_d<7>(P, masked, P.nbatches, smem, st, c.sm_count); break;
     case 8: e = launch_gibbs_d<8>(P, masked, P.nbatches, smem, st, c.sm_count); break;
+#endif
   }
   if (e != cudaSuccess) KDE_FAIL(100 + (int)e, "gibbs kernel launch: %s", cudaGetErrorString(e));
   if (launches) *launches += 1;
