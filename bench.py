@@ -159,7 +159,7 @@ def main():
     import torch
     import torch.distributed as dist
     import kde_b200 as K
-    from kde_b200 import _lib, api as _api
+    from kde_b200 import _lib, api as _api, dist as _dist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -185,18 +185,15 @@ def main():
     dev = torch.device("cuda", local)
     d_pts = torch.empty((n_per, DIM), dtype=torch.float64, device=dev)
     d_idx = torch.empty((n_per, NDENS), dtype=torch.int64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    g_pts = g_idx = None
     if world > 1:
         g_pts = torch.empty((Np_total, DIM), dtype=torch.float64, device=dev)
         g_idx = torch.empty((Np_total, NDENS), dtype=torch.int64, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def step():
-        st = torch.cuda.current_stream().cuda_stream
-        _lib.check(L.kdeb200_gibbs_device(handles, NDENS, Np_total, NITER, 1, None, None, 0, None, 0, SEED, s0, s1,
-                                          d_pts.data_ptr(), d_idx.data_ptr(), st))
-        if world > 1:
-            dist.all_gather_into_tensor(g_pts, d_pts)
-            dist.all_gather_into_tensor(g_idx, d_idx)
+    def step():  # the sharded product: this rank's block + NCCL all-gather (kde_b200.dist)
+        _dist.prod_sharded_device(handles, NDENS, DIM, Np_total, NITER, SEED, d_pts, d_idx, g_pts, g_idx)
 
     def barrier():
         if world > 1:

@@ -188,6 +188,7 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
 
   // uniform leaf bandwidth is what the typed constructors of the reference always produce
   for (int k = 0; k < d; ++k) t->hvar[k] = bandwidth[N * d + k];
+  for (int k = 0; k < d; ++k) t->root_mean[k] = means[k];
   for (int64_t i = N; i < NN; ++i)
     for (int k = 0; k < d; ++k)
       if (bandwidth[i * d + k] != t->hvar[k]) {
@@ -323,6 +324,7 @@ int tree_destroy(kdeb200_tree_t t) {
   cudaFree(t->d_labels);
   cudaFree(t->d_leaf);
   cudaFree(t->d_perm);
+  if (t->d_leaf32) cudaFree(t->d_leaf32);
   delete t;
   return 0;
 }

@@ -25,6 +25,7 @@ struct kdeb200_tree_s {
   int64_t N = 0;
   bool degenerate = false;  // some bandwidth <= 0 or non-finite value: fast arithmetic not valid
   double hvar[KDEB200_MAX_DIM] = {0};  // the uniform leaf variances (bandwidthMin/Max[1:d])
+  double root_mean[KDEB200_MAX_DIM] = {0};  // mean of node 1 (centre of the FP32 coordinates)
   int SA = 0, SC = 0, SE = 0;          // record strides in doubles (even => 16-byte aligned records)
   std::vector<kdeb200::Level> levels;  // levels[0] = {root}; levels[l], l = 1..depth
   int depth = 0;                       // last distinct level (all leaves)
@@ -33,5 +34,6 @@ struct kdeb200_tree_s {
   int64_t *d_labels = nullptr;  // deepest level, level order: permutation + 1 (src/MSGibbs01.jl:615)
   double *d_leaf = nullptr;     // leaf order (N+1..2N): [x_0..x_{d-1}, w], stride SE -- evalDirect's order
   int64_t *d_perm = nullptr;    // leaf order: original 0-based index
+  float *d_leaf32 = nullptr;    // lazily built FP32 shadow of d_leaf (centred, pre-scaled), eval_f32.cu
   size_t device_bytes = 0;
 };

@@ -1,0 +1,92 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: block partition, global-index
+addressing of the random streams, all-gather of uneven blocks, all-reduce of the LOO likelihood.
+The per-shard worker is the oracle here (no GPU in this container); tests/test_gpu_dist.py runs the
+same logic with the CUDA worker."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from kde_b200 import dist as kd
+from oracle import oracle as O
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make():
+    rng = np.random.default_rng(42)
+    pts = [rng.standard_normal((2, 60)) + j for j in range(3)]
+    return rng, pts
+
+
+def _worker(rank, world, port, Np, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng, pts = _make()
+        trees = [O.OKDE.kde_bw(p, [0.3, 0.4]) for p in pts]
+        T = 3
+        nU, nN = O.prod_sizes(trees, Np, T)
+        U, G = rng.random(nU), rng.standard_normal(nN)
+        full_p, full_i = O.gibbs(trees, Np, T, U, G)
+
+        def gibbs_shard(a, b):
+            p, i = O.gibbs(trees, Np, T, U, G, s0=a, s1=b)
+            return p[:, a:b], i[:, a:b]
+
+        gp, gi = kd.prod_sharded(None, Np, compute=gibbs_shard)
+        assert gp.shape == full_p.shape and np.array_equal(gp, full_p) and np.array_equal(gi, full_i)
+
+        pos = rng.standard_normal((2, 37))
+        full_e = trees[0].evaluate(pos)
+        ge = kd.eval_sharded(None, pos, compute=lambda a, b: trees[0].evaluate(pos[:, a:b]) if b > a else np.zeros(0))
+        assert np.array_equal(ge, full_e)
+
+        t = trees[1]
+        arr = t.arrays()
+        N = t.npts
+        L = t.evaluate()                       # original order
+        perm = arr["permutation"][N:] - 1      # leaf row -> original index
+        W = arr["weights"][N:]
+
+        def loo_rows(a, b):
+            return float(np.sum(np.log(L[perm[a:b]]) * W[a:b])), 0
+
+        class BD:  # minimal stand-in: only the row count is read when compute is injected
+            pass
+        H = kd.loo_entropy_sharded(BD(), compute=loo_rows, n_rows=N)
+        assert abs(H - t.entropy()) < 1e-12 * abs(t.entropy())
+        Hinf = kd.loo_entropy_sharded(BD(), compute=lambda a, b: (0.0, 1 if rank == 1 else 0), n_rows=N)
+        assert Hinf == float("inf")
+        if rank == 0:
+            out.put("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("Np", [40, 101])
+def test_sharded_paths_world2(Np):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    mp.spawn(_worker, args=(2, free_port(), Np, q), nprocs=2, join=True)
+    assert q.get(timeout=5) == "ok"
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 100, 1_000_003):
+        for w in (1, 2, 3, 8):
+            r = [kd.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1

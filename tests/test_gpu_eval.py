@@ -106,3 +106,17 @@ def test_errors():
         K.evaluateDualTree(p, np.zeros((2, 4)), addop=(lambda a, b: a + b,))
     with pytest.raises(K.KDEError):
         K.kde(np.zeros((9, 5)) + np.arange(5), [1.0])._dev()
+
+
+@pytest.mark.parametrize("d,N,M", [(1, 300, 500), (2, 1000, 333), (3, 4096, 1000), (4, 513, 64), (6, 200, 129)])
+def test_fp32_variant_within_1e5(d, N, M):
+    """FP32 (MUFU ex2) variant: 1e-5 relative (BASELINE.json north_star)."""
+    rng = np.random.default_rng(300 + d + N)
+    pts = mixture(rng, d, N)
+    bw = silverman(pts)
+    pos = mixture(rng, d, M)
+    p, o = K.kde(pts, bw), OKDE.kde_bw(pts, bw)
+    exp = o.evaluate(pos)
+    got = K.evaluateDualTree(p, pos, precision=K.F32)
+    assert relerr(got, exp) < 1e-5
+    assert relerr(K.evaluateDualTree(p, p, precision=K.F32), o.evaluate()) < 1e-5
