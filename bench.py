@@ -54,6 +54,13 @@ def silverman(pts):
     return pts.std(axis=1, ddof=1) * (4.0 / ((d + 2.0) * N)) ** (1.0 / (d + 4.0))
 
 
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -103,7 +110,7 @@ def run_reference(args, rank, world):
         return
     from oracle import oracle as O
     trees = [O.OKDE.kde_bw(synth_points(j), silverman(synth_points(j))) for j in range(NDENS)]
-    cores = O.max_threads()
+    cores = host_cores()  # torchrun exports OMP_NUM_THREADS=1: ask the OS instead
     n = args.ref_samples if args.ref_samples > 0 else 16 * cores
     nU, nN = O.prod_sizes(trees, n, NITER)
     rng = np.random.default_rng(SEED)
@@ -279,7 +286,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             from oracle import oracle as O
             otrees = [O.OKDE.kde_bw(p, silverman(p)) for p in pts]
-            cores = O.max_threads()
+            cores = host_cores()
             rng = np.random.default_rng(SEED)
             n0 = 2 * cores
             nU, nN = O.prod_sizes(otrees, n0, NITER)

@@ -1,0 +1,123 @@
+# KDEB200.jl -- Julia `ccall` binding of libkdeb200.so (include/kdeb200.h).
+#
+# NOT RUNNABLE IN THE BUILD IMAGE (no julia binary there); it is the binding a maintainer of
+# KernelDensityEstimate.jl adds to re-point the three seams of SURVEY.md 8b at the B200 library.
+# kerneldensityestimate.jl_b200/api.py is the line-for-line Python mirror that the test-suite
+# exercises; keep the two in sync.
+#
+#   seam S1  gibbs1(...)                 src/MSGibbs01.jl:527-629  ->  KDEB200.gibbs1!
+#   seam S2  evaluate(bd, loc, p, ...)   src/DualTree01.jl:303-346 ->  KDEB200.evaluate!
+#   seam S3  entropy(bd) / nLOO_LL       src/DualTree01.jl:505-508, src/CrossValidation.jl:15-24
+#                                                                    ->  KDEB200.entropy
+module KDEB200
+
+using KernelDensityEstimate
+const KDE = KernelDensityEstimate
+
+const LIB = get(ENV, "KDEB200_LIB", "libkdeb200.so")
+
+# nonzero return code -> the reference's error convention (error(...) => ErrorException)
+function check(rc::Cint)
+  rc == 0 && return nothing
+  error(unsafe_string(ccall((:kdeb200_last_error, LIB), Cstring, ())))
+end
+
+init(device::Integer=0) = check(ccall((:kdeb200_init, LIB), Cint, (Cint,), device))
+
+# ---- S0: device-resident BallTreeDensity -------------------------------------------------
+mutable struct DeviceTree
+  h::Ptr{Cvoid}
+  function DeviceTree(bd::BallTreeDensity)
+    bd.multibandwidth == 0 || error("kdeb200: multibandwidth != 0 is not supported")
+    bt = bd.bt
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve bd begin
+      check(ccall((:kdeb200_tree_create, LIB), Cint,
+                  (Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64},
+                   Ref{Ptr{Cvoid}}),
+                  bt.dims, bt.num_points, bd.means, bd.bandwidth, bt.weights, bt.left_child, bt.right_child,
+                  bt.permutation, out))
+    end
+    t = new(out[])
+    finalizer(x -> ccall((:kdeb200_tree_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), t)
+    return t
+  end
+end
+
+euclidean(addop, diffop) = all(f -> f === (+), addop) && all(f -> f === (-), diffop)
+
+# ---- S1: gibbs1 -------------------------------------------------------------------------
+# Same positional arguments as KDE.gibbs1; writes pts (d*Np) and ind (Ndens x Np) in place.
+# randU / randN === nothing selects the library's Philox streams (keyed by `seed`).
+function gibbs1!(Ndens::Int, trees::Vector{BallTreeDensity}, Np::Int, Niter::Int,
+                 pts::Vector{Float64}, ind::Matrix{Int},
+                 randU::Union{Nothing,Vector{Float64}}, randN::Union{Nothing,Vector{Float64}};
+                 addop=(+,), diffop=(-,), getMu=(KDE.getEuclidMu,), getLambda=(KDE.getEuclidLambda,),
+                 addEntropy::Bool=true, ndims::Int=maximum(Ndim.(trees)),
+                 partialDimMask::AbstractVector{<:BitVector}=[trues(ndims) for i in 1:Ndens],
+                 seed::UInt64=rand(UInt64))
+  (euclidean(addop, diffop) && all(f -> f === KDE.getEuclidMu, getMu) &&
+   all(f -> f === KDE.getEuclidLambda, getLambda)) ||
+    error("kdeb200: only the default Euclidean (+,-) manifold is supported on the B200 path")
+  dts = [DeviceTree(t) for t in trees]
+  hs = Ptr{Cvoid}[d.h for d in dts]
+  mask = UInt8[partialDimMask[j][k] ? 0x01 : 0x00 for k in 1:ndims, j in 1:Ndens]  # [j*d + k], column-major
+  uptr = randU === nothing ? Ptr{Float64}(C_NULL) : pointer(randU)
+  nptr = randN === nothing ? Ptr{Float64}(C_NULL) : pointer(randN)
+  GC.@preserve dts hs mask randU randN pts ind begin
+    check(ccall((:kdeb200_gibbs, LIB), Cint,
+                (Ptr{Ptr{Cvoid}}, Cint, Int64, Cint, Cint, Ptr{UInt8}, Ptr{Float64}, Int64, Ptr{Float64}, Int64,
+                 UInt64, Int64, Int64, Ptr{Float64}, Ptr{Int64}),
+                hs, Ndens, Np, Niter, addEntropy, mask, uptr, randU === nothing ? 0 : length(randU),
+                nptr, randN === nothing ? 0 : length(randN), seed, 0, Np, pts, ind))
+  end
+  nothing
+end
+
+# ---- S2: evaluate -------------------------------------------------------------------------
+# p is filled in the original order of `locations`' points (bd === locations => leave-one-out).
+function evaluate!(bd::BallTreeDensity, locations::BallTreeDensity, p::Vector{Float64},
+                   maxErr::Float64=1e-3, addop=(+,), diffop=(-,); precision::Int=0)
+  bd.bt.dims == locations.bt.dims || error("evaluate -- dimensions of two BallTreeDensities must match")
+  euclidean(addop, diffop) || error("kdeb200: only the default Euclidean (+,-) manifold is supported")
+  dt = DeviceTree(bd)
+  if bd === locations
+    GC.@preserve dt p check(ccall((:kdeb200_eval, LIB), Cint,
+      (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Cint, Ptr{Float64}), dt.h, C_NULL, Npts(bd), 1, precision, p))
+  else
+    pos = getPoints(locations)   # d x M, original order
+    GC.@preserve dt pos p check(ccall((:kdeb200_eval, LIB), Cint,
+      (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Cint, Ptr{Float64}), dt.h, pos, size(pos, 2), 0, precision, p))
+  end
+  nothing
+end
+
+function evaluateDualTree(bd::BallTreeDensity, pos::Matrix{Float64}, lvFlag::Bool=false; precision::Int=0)
+  bd.bt.dims == size(pos, 1) || error("bd and pos must have the same dimension")
+  dt = DeviceTree(bd)
+  M = lvFlag ? Npts(bd) : size(pos, 2)
+  p = zeros(M)
+  GC.@preserve dt pos p check(ccall((:kdeb200_eval, LIB), Cint,
+    (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Cint, Ptr{Float64}), dt.h, pos, M, lvFlag, precision, p))
+  return p
+end
+
+# ---- S3: leave-one-out entropy (one launch, one scalar back) ------------------------------------
+function entropy(bd::BallTreeDensity, dt::DeviceTree=DeviceTree(bd))
+  H = Ref{Float64}(0.0)
+  bw = bd.bandwidthMin[1:bd.bt.dims]     # the (possibly alpha^2-scaled) leaf variances
+  GC.@preserve dt bw check(ccall((:kdeb200_loo_entropy, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}),
+                                 dt.h, bw, H))
+  return H[]
+end
+
+# nLOO_LL with the device tree reused across the ~20 golden-section steps of one ksize call
+function nLOO_LL(alpha::Float64, bd::BallTreeDensity, dt::DeviceTree)
+  a2 = alpha^2
+  KDE.updateBandwidth!(bd, bd.bandwidth * a2)
+  H = entropy(bd, dt)
+  KDE.updateBandwidth!(bd, bd.bandwidth / a2)
+  return H
+end
+
+end # module
