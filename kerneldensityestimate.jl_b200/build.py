@@ -6,7 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkdeb200.so")
-SOURCES = ["context.cu", "tree.cu", "eval.cu", "eval_f32.cu", "gibbs.cu", "peaks.cu", "capi.cu"]
+SOURCES = ["context.cu", "tree.cu", "eval.cu", "eval_f32.cu", "gibbs.cu", "peaks.cu", "capi.cu"] + [
+    "gibbs_d%d.cu" % d for d in range(1, 9)]
+GIBBS_TUNED = ["gibbs.cu", "gibbs_d3.cu"]  # what the tuning variants rebuild (GB_ONLY_D3)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-ccbin", "/usr/bin/g++", "-Xptxas", "-v"]
@@ -29,8 +31,9 @@ def build_variant(tag, defines):
     procs, objs = [], []
     build()
     for s in SOURCES:
-        if s != "gibbs.cu":  # the tuning knobs only touch the Gibbs kernel
-            objs.append(os.path.join(HERE, "build", s.replace(".cu", ".o")))
+        if s not in GIBBS_TUNED:  # the tuning knobs only touch the Gibbs kernel
+            if not s.startswith("gibbs_d"):
+                objs.append(os.path.join(HERE, "build", s.replace(".cu", ".o")))
             continue
         o = os.path.join(bdir, s.replace(".cu", ".o"))
         objs.append(o)

@@ -88,23 +88,22 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t sample, 
 }
 
 // ---------------------------------------------------------------- FP64 exp --------------
-// exp(x) = 2^(n >> 6) * T[n & 63] * e^r,  n = rint(x*64/ln2), |r| <= ln2/128.
-// 10 FP64-pipe instructions (stock exp(): 14 DFMA + 2 DADD + 1 DMUL) + one shared-memory table
-// load; truncation error r^6/720 <= 3.5e-17, total error ~1 ulp.  The core is branch-free so that
-// independent evaluations interleave in one basic block (the FP64 pipe needs >= 4 independent
-// chains per scheduler); coefficients sit in the constant bank so DFMA reads them as operands.
-#define KDE_EXP_TAB 64
+#define KDE_EXP_TAB 256
 __constant__ double kExpC[8] = {
-    92.33248261689366,       // 64/ln2
-    6755399441055744.0,      // 1.5 * 2^52
-    -1.0830424696249145e-02, // -ln2/64 (rounded)
-    -3.623510646634843e-19,  // -(ln2/64 - rounded), from 60-digit ln2
-    8.3333333333333332e-03,  // 1/120
+    369.3299304675746,      // 256/ln2
+    6755399441055744.0,      // 1.5 * 2^52: the low word of x*256/ln2 + this is n = rint(x*256/ln2)
+    -0.0027076061740622863,  // -ln2/256 (rounded)
+    -9.058776616587108e-20,  // -(ln2/256 - rounded), from 60-digit ln2
     4.1666666666666664e-02,  // 1/24
     1.6666666666666666e-01,  // 1/6
-    0.5};
+    0.5,
+    0.0};
 
-// valid for |x| <= 700 (normal results); anything else must be fixed up by the caller
+// exp(x) = 2^(n >> 8) * T[n & 255] * e^r,  n = rint(x*256/ln2), |r| <= ln2/512: degree-4 Taylor
+// (truncation r^5/120 <= 3.8e-17), 9 FP64-pipe instructions (libdevice exp(): 17) + 4 integer ops + one
+// shared-memory table load; ~1 ulp.  Valid for |x| <= 700 (normal results); anything else must be
+// fixed up by the caller.  Branch-free so that independent evaluations interleave in one basic
+// block; coefficients sit in the constant bank so DFMA reads them as operands.
 __device__ __forceinline__ double kde_exp_core(double x, const double *__restrict__ tab) {
   const double t = __fma_rn(x, kExpC[0], kExpC[1]);
   const int n = __double2loint(t);
@@ -113,12 +112,12 @@ __device__ __forceinline__ double kde_exp_core(double x, const double *__restric
   r = __fma_rn(nf, kExpC[3], r);
   double q = __fma_rn(r, kExpC[4], kExpC[5]);
   q = __fma_rn(q, r, kExpC[6]);
-  q = __fma_rn(q, r, kExpC[7]);
   const double r2 = __dmul_rn(r, r);
   const double p = __fma_rn(q, r2, r);
   const double T = tab[n & (KDE_EXP_TAB - 1)];
   const double y = __fma_rn(T, p, T);
-  return __hiloint2double(__double2hiint(y) + (n & ~(KDE_EXP_TAB - 1)) * 16384, __double2loint(y));  // + (n>>6)<<20
+  // exponent: (n >> 8) << 20 == (n & ~255) << 12
+  return __hiloint2double(__double2hiint(y) + (n & ~(KDE_EXP_TAB - 1)) * 4096, __double2loint(y));
 }
 
 // Gibbs flavour: x < -700 (p < 1e-304) is clamped (or flushed to 0 with KDE_FLUSH_SELECT), negative NaN -> tiny

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
   __shared__ __align__(8) uint64_t bars[EV_STAGES];
 
   const int tid = threadIdx.x;
-  if (tid < KDE_EXP_TAB) tab[tid] = P.exptab[tid];
+  for (int i = tid; i < KDE_EXP_TAB; i += EV_THREADS) tab[i] = P.exptab[i];
   if (tid == 0) {
     for (int s = 0; s < EV_STAGES; ++s) mbar_init(&bars[s], 1);
     mbar_fence_init();

@@ -1,0 +1,5 @@
+// gibbs_d6.cu -- explicit instantiation of the Gibbs kernel for d = 6 (both mask variants).
+#include "gibbs_kernel.cuh"
+namespace kdeb200 {
+template cudaError_t launch_gibbs_d<6>(const GibbsParams &, bool, int, size_t, cudaStream_t, int);
+}

@@ -1,0 +1,545 @@
+// gibbs_kernel.cuh -- K1: the multiscale Gibbs KDE-product sampler as one kernel (device code and
+// launch template; gibbs.cu holds the host side, gibbs_d<N>.cu one explicit instantiation per d).
+//
+// Computes what gibbs1 (src/MSGibbs01.jl:527-629) computes for every output sample:
+// levelInit!/initIndices! :467-497, samplePoint! :440-463 (gaussianProductMeanCov! :176-216),
+// levelDown! :500-523, sampleIndices! :364-385, sampleIndex :404-429 (makeFasterSampleIndex!
+// :250-328, selectLabelOnLevel :330-351, updateGlbParticlesVariance! :89-115), labels :612-616.
+//
+// Mapping (DESIGN.md "K1"): ONE THREAD PER CHAIN.  All chains execute the same static schedule
+// of label draws (level, pass, density), so a CTA streams each level's node records once through
+// a 3-stage shared-memory ring filled by 1-D TMA bulk copies and every lane reads the same record
+// (broadcast LDS).  A draw is two passes: pass 1 accumulates the unnormalised weights p[z]
+// SEQUENTIALLY in the reference's node order (identical summation order => identical pT and CDF
+// up to exp rounding) and checkpoints the running sum every G nodes (<= 64 checkpoints, local
+// memory); pass 2 re-evaluates only the chunk that contains u * pT, from global memory.
+// The arithmetic of one kernel evaluation is restructured:
+//   leaf levels (uniform bandwidth): 1/c_k and the normaliser hoisted out of the node loop,
+//     ln w folded into the exponent                       -> 3d + 11 FP64-pipe instr / node
+//   internal levels, sampleIndices!: -0.5/b_k and ln w - 0.5 sum ln b_k precomputed per node
+//   internal levels, sampleIndex   : c_k = b_k + Calmost_k, sum_k ln c_k -> one rsqrt(prod c_k)
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#pragma once
+#include "tree.cuh"
+
+namespace kdeb200 {
+
+constexpr int GB_THREADS = 128;
+constexpr int GB_STAGES = 3;
+constexpr int GB_TILE_BYTES = 8192;
+constexpr int GB_MAXCK = 64;  // checkpoints per draw
+#ifndef GB_UNROLL_A
+#define GB_UNROLL_A 4
+#endif
+#ifndef GB_UNROLL_C
+#define GB_UNROLL_C 2
+#endif
+#ifndef GB_MINBLOCKS
+#define GB_MINBLOCKS 4
+#endif
+
+enum : int { VAR_A = 0, VAR_B = 1, VAR_C = 2 };
+
+struct alignas(16) Draw {
+  const double *rec;        // evaluation records of this level (variant-specific layout)
+  const double *rec_state;  // records the chain state is refreshed from ([m.., lnw] or [m.., b.., lnw])
+  const double *wts;        // raw weights (fallback path)
+  int n;                    // nodes on the level
+  int stride;               // doubles per evaluation record
+  int state_stride;
+  int G;                    // checkpoint chunk (power of two)
+  int nchunks;
+  int tnodes;               // nodes per tile (power of two)
+  int ntiles;
+  int tile0;                // first tile of this draw in the per-sample tile stream
+  short j;                  // density
+  signed char variant;      // VAR_A / VAR_B / VAR_C
+  signed char kind;         // 0: sampleIndices! (against X), 1: sampleIndex (leave-one-out product)
+  signed char state_has_bw; // rec_state carries per-node variances
+  signed char new_level;    // first draw of a level: samplePoint! comes first
+  short level;              // 1-based level
+};
+
+struct alignas(16) TileDesc {
+  const double *src;
+  uint32_t bytes;
+  uint32_t pad;
+};
+
+struct GibbsParams {
+  const Draw *draws;
+  const TileDesc *tiles;
+  const double *exptab;
+  const double *randU, *randN;  // injected streams or null (Philox)
+  double *points;               // d x (s1-s0)
+  int64_t *indices;             // M x (s1-s0)
+  int64_t s0, s1, perU, perN;
+  uint64_t seed;
+  int ndraws, ntiles, M, L, T, add_entropy, nbatches;
+  const double *root_rec[KDEB200_MAX_DENS];  // [m.., b.., lnw] of node 1
+  const int64_t *labels[KDEB200_MAX_DENS];   // deepest level: permutation + 1
+  double hvar[KDEB200_MAX_DENS][KDEB200_MAX_DIM];
+  unsigned char mask[KDEB200_MAX_DENS][KDEB200_MAX_DIM];   // partialDimMask[j][k]
+  unsigned char other[KDEB200_MAX_DENS][KDEB200_MAX_DIM];  // OR_{i != j} mask[i][k]
+};
+
+// ---- one kernel evaluation, three record layouts -----------------------------------------
+// Explicit rn intrinsics: pass 1 and pass 2 must produce bit-identical p[z].
+template <int D, bool MASK>
+struct Hoist {
+  double mu[D];    // X or Malmost
+  double ich[D];   // variant A: -0.5 / (h_k + Calmost_k)
+  double cadd[D];  // variant C: Calmost_k
+  bool act[D];     // dimension participates (partialDimMask logic, :270-285)
+};
+
+// record -> registers with 16-byte loads (records are 16-byte aligned, strides are even)
+template <int S>
+__device__ __forceinline__ void load_rec(const double *__restrict__ r, double (&rr)[S]) {
+#pragma unroll
+  for (int k = 0; k < S; k += 2) {
+    const double2 v = *reinterpret_cast<const double2 *>(r + k);
+    rr[k] = v.x;
+    rr[k + 1] = v.y;
+  }
+}
+
+// One evaluation is split in two stages so that pass 1 can software-pipeline them (stage 1 of
+// node group g overlaps the exp chains of group g-1 in one basic block):
+//   pre_*: record -> exponent argument (and, variant C, the normaliser rsqrt(prod c_k))
+//   fin  : p = exp(arg) [* scale]
+template <int D, bool MASK>
+__device__ __forceinline__ void pre_A(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg, double &sc) {
+  constexpr int S = (D + 2) & ~1;
+  double rr[S];
+  load_rec<S>(r, rr);
+  double acc = rr[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    if (MASK && !h.act[k]) continue;
+    const double df = __dadd_rn(rr[k], -h.mu[k]);
+    acc = __fma_rn(__dmul_rn(df, df), h.ich[k], acc);
+  }
+  arg = acc;
+  sc = 1.0;
+}
+
+template <int D, bool MASK>
+__device__ __forceinline__ void pre_B(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg, double &sc) {
+  constexpr int S = (2 * D + 2) & ~1;
+  double rr[S];
+  load_rec<S>(r, rr);
+  double acc = rr[2 * D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double df = __dadd_rn(rr[k], -h.mu[k]);
+    acc = __fma_rn(__dmul_rn(df, df), rr[D + k], acc);
+  }
+  arg = acc;
+  sc = 1.0;
+}
+
+template <int D, bool MASK>
+__device__ __forceinline__ void pre_C(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg, double &sc) {
+  constexpr int S = (2 * D + 2) & ~1;
+  double rr[S];
+  load_rec<S>(r, rr);
+  if (D == 3 && !MASK) {
+    // one MUFU.RSQ64H for the normaliser AND the three reciprocals:
+    //   rs = rsqrt(c0 c1 c2), R = rs^2 = 1/(c0 c1 c2), 1/c_k = R * prod_{i != k} c_i   (38 FP64 instr / node)
+    const double c0 = __dadd_rn(rr[3], h.cadd[0]), c1 = __dadd_rn(rr[4], h.cadd[1]), c2 = __dadd_rn(rr[5], h.cadd[2]);
+    const double d0 = __dadd_rn(rr[0], -h.mu[0]), d1 = __dadd_rn(rr[1], -h.mu[1]), d2 = __dadd_rn(rr[2], -h.mu[2]);
+    const double c01 = __dmul_rn(c0, c1);
+    const double rs = kde_rsqrt(__dmul_rn(c01, c2));
+    const double Rv = __dmul_rn(rs, rs);
+    const double t = __dmul_rn(c2, Rv);
+    double quad = __dmul_rn(__dmul_rn(d2, d2), __dmul_rn(c01, Rv));
+    quad = __fma_rn(__dmul_rn(d0, d0), __dmul_rn(c1, t), quad);
+    quad = __fma_rn(__dmul_rn(d1, d1), __dmul_rn(c0, t), quad);
+    arg = __fma_rn(quad, -0.5, rr[6]);
+    sc = rs;
+    return;
+  }
+  double quad = 0.0;
+  double prod = 1.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    if (MASK && !h.act[k]) continue;
+    const double c = __dadd_rn(rr[D + k], h.cadd[k]);
+    const double df = __dadd_rn(rr[k], -h.mu[k]);
+    quad = __fma_rn(__dmul_rn(df, df), kde_rcp(c), quad);
+    prod = __dmul_rn(prod, c);
+  }
+  arg = __fma_rn(quad, -0.5, rr[2 * D]);
+  sc = kde_rsqrt(prod);
+}
+
+template <int D, bool MASK, int VAR>
+__device__ __forceinline__ void pre_node(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg,
+                                         double &sc) {
+  if (VAR == VAR_A) pre_A<D, MASK>(r, h, arg, sc);
+  else if (VAR == VAR_B) pre_B<D, MASK>(r, h, arg, sc);
+  else pre_C<D, MASK>(r, h, arg, sc);
+}
+
+template <int VAR>
+__device__ __forceinline__ double fin_node(double arg, double sc, const double *__restrict__ tab) {
+  const double e = kde_exp_flush(arg, tab);
+  return (VAR == VAR_C) ? __dmul_rn(e, sc) : e;
+}
+
+template <int D, bool MASK, int VAR>
+__device__ __forceinline__ double eval_node(const double *__restrict__ r, const Hoist<D, MASK> &h,
+                                            const double *__restrict__ tab) {
+  double arg, sc;
+  pre_node<D, MASK, VAR>(r, h, arg, sc);
+  return fin_node<VAR>(arg, sc, tab);
+}
+
+// pass 1 over the tiles of one draw: sequential sum, checkpoints every G nodes
+struct Ring {
+  double *tiles;
+  uint64_t *bars;
+  const TileDesc *descs;
+  int64_t total;  // tiles this CTA will consume over its whole life
+  int ntiles;     // tiles per sample schedule
+};
+
+__device__ __forceinline__ void ring_issue(const Ring &R, int64_t q) {
+  const TileDesc td = R.descs[(int)(q % R.ntiles)];
+  uint64_t *bar = &R.bars[q % GB_STAGES];
+  mbar_expect_tx(bar, td.bytes);
+  tma_bulk_g2s(R.tiles + (size_t)(q % GB_STAGES) * (GB_TILE_BYTES / 8), td.src, td.bytes, bar);
+}
+
+// consume one pipelined group: p = exp(arg)[*sc], sequential adds, checkpoint at chunk ends
+template <int VAR, int UNR>
+__device__ __forceinline__ void consume_group(const double (&arg)[UNR], const double (&sc)[UNR],
+                                              const double *__restrict__ tab, double &S, int &consumed, int &c,
+                                              double *__restrict__ ck, int G, int n) {
+  double p[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) p[u] = fin_node<VAR>(arg[u], sc[u], tab);
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) S = __dadd_rn(S, p[u]);
+  consumed += UNR;
+  if ((consumed & (G - 1)) == 0 || consumed == n) ck[c++] = S;
+}
+
+template <int D, bool MASK, int VAR>
+__device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h, const double *__restrict__ tab,
+                                        const Ring &R, int64_t &q, double *__restrict__ ck) {
+  // UNR nodes per group.  Within a tile the groups are software-pipelined with two register sets
+  // (A/B ping-pong, no rotation moves): stage 1 (record -> exponent) of group g is issued in the
+  // same basic block as the exp chains of group g-1.  Fewer nodes per group at high d, where ptxas
+  // 12.9 segfaults on wide unrolls.
+  constexpr int UNR = (D <= 4) ? ((VAR == VAR_C) ? GB_UNROLL_C : GB_UNROLL_A) : (D <= 5 ? 2 : 1);
+  constexpr int DG = 2 * UNR;
+  constexpr int stride = (VAR == VAR_A) ? ((D + 2) & ~1) : ((2 * D + 2) & ~1);  // == dr.stride
+  const int n = dr.n, G = dr.G;
+  double S = 0.0;
+  int c = 0;
+  int consumed = 0;
+  for (int t = 0; t < dr.ntiles; ++t, ++q) {
+    const int cnt = (n - consumed < dr.tnodes) ? (n - consumed) : dr.tnodes;
+    mbar_wait(&R.bars[q % GB_STAGES], (uint32_t)((q / GB_STAGES) & 1));
+    const double *rec = R.tiles + (size_t)(q % GB_STAGES) * (GB_TILE_BYTES / 8);
+    int z = 0;
+    if (D <= 6 && G >= UNR && cnt >= DG) {  // checkpoints fall on group boundaries (d >= 7: ptxas 12.9 segfaults on the pipelined body)
+      const int full = cnt & ~(DG - 1);
+      double a0[UNR], s0[UNR], a1[UNR], s1[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) pre_node<D, MASK, VAR>(rec + (size_t)u * stride, h, a0[u], s0[u]);
+      for (; z + DG < full; z += DG) {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) pre_node<D, MASK, VAR>(rec + (size_t)(z + UNR + u) * stride, h, a1[u], s1[u]);
+        consume_group<VAR, UNR>(a0, s0, tab, S, consumed, c, ck, G, n);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) pre_node<D, MASK, VAR>(rec + (size_t)(z + DG + u) * stride, h, a0[u], s0[u]);
+        consume_group<VAR, UNR>(a1, s1, tab, S, consumed, c, ck, G, n);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) pre_node<D, MASK, VAR>(rec + (size_t)(z + UNR + u) * stride, h, a1[u], s1[u]);
+      consume_group<VAR, UNR>(a0, s0, tab, S, consumed, c, ck, G, n);
+      consume_group<VAR, UNR>(a1, s1, tab, S, consumed, c, ck, G, n);
+      z = full;
+    }
+    for (; z < cnt; ++z) {  // small levels and the ragged end of the last tile: one node at a time
+      S = __dadd_rn(S, eval_node<D, MASK, VAR>(rec + (size_t)z * stride, h, tab));
+      consumed += 1;
+      if ((consumed & (G - 1)) == 0 || consumed == n) ck[c++] = S;
+    }
+    __syncthreads();  // stage free again
+    if (threadIdx.x == 0 && q + GB_STAGES < R.total) ring_issue(R, q + GB_STAGES);
+  }
+  return S;
+}
+
+// pass 2: locate the first z with target <= prefix(z) inside chunk cs (per-lane global loads)
+template <int D, bool MASK, int VAR>
+__device__ __forceinline__ int pass2(const Draw &dr, const Hoist<D, MASK> &h, const double *__restrict__ tab, int cs,
+                                  double S, double target) {
+  constexpr int stride = (VAR == VAR_A) ? ((D + 2) & ~1) : ((2 * D + 2) & ~1);  // == dr.stride
+  const int z0 = cs * dr.G;
+  const int z1 = (z0 + dr.G < dr.n) ? z0 + dr.G : dr.n;
+  const double *r = dr.rec + (size_t)z0 * stride;
+  int zs = z1 - 1;
+  bool found = false;
+  for (int z = z0; z < z1; ++z) {
+    S = __dadd_rn(S, eval_node<D, MASK, VAR>(r, h, tab));
+    if (!found && target <= S) {
+      zs = z;
+      found = true;
+    }
+    r += stride;
+  }
+  return zs;
+}
+
+template <int D, bool MASK>
+__global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const __grid_constant__ GibbsParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tiles = reinterpret_cast<double *>(smem_raw);
+  __shared__ __align__(16) double tab[KDE_EXP_TAB];
+  __shared__ __align__(8) uint64_t bars[GB_STAGES];
+  const int tid = threadIdx.x;
+  const int M = P.M;
+
+  for (int i = tid; i < KDE_EXP_TAB; i += GB_THREADS) tab[i] = P.exptab[i];
+  if (tid == 0) {
+    for (int s = 0; s < GB_STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  int nb_local = 0;
+  for (int b = blockIdx.x; b < P.nbatches; b += gridDim.x) ++nb_local;
+  Ring R;
+  R.tiles = tiles;
+  R.bars = bars;
+  R.descs = P.tiles;
+  R.ntiles = P.ntiles;
+  R.total = (int64_t)nb_local * P.ntiles;
+  if (tid == 0)
+    for (int64_t q0 = 0; q0 < GB_STAGES && q0 < R.total; ++q0) ring_issue(R, q0);
+  int64_t q = 0;
+
+  // chain state: lambda = 1/variance and lambda*mu of the currently selected node of each density
+  double lam[KDEB200_MAX_DENS * D];
+  double lmu[KDEB200_MAX_DENS * D];
+  double ck[GB_MAXCK];
+  int selpos[KDEB200_MAX_DENS];
+
+  for (int batch = blockIdx.x; batch < P.nbatches; batch += gridDim.x) {
+    int64_t s = P.s0 + (int64_t)batch * GB_THREADS + tid;
+    const bool live = s < P.s1;
+    if (!live) s = P.s1 - 1;  // idle lanes replay the last chain (keeps the CTA in lock-step)
+
+    // levelInit!/initIndices!/calcIndices!: every density starts at the root
+    for (int j = 0; j < M; ++j) {
+      const double *rr = P.root_rec[j];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        if (MASK && !P.mask[j][k]) {
+          lam[j * D + k] = 0.0;
+          lmu[j * D + k] = 0.0;
+        } else {
+          const double l = 1.0 / rr[D + k];
+          lam[j * D + k] = l;
+          lmu[j * D + k] = rr[k] * l;
+        }
+      }
+      selpos[j] = 0;
+    }
+
+    double X[D];
+    for (int di = 0; di < P.ndraws; ++di) {
+      const Draw dr = P.draws[di];
+      const int j = dr.j;
+
+      if (dr.new_level) {  // samplePoint!(addEntropy = true) with normals g(level-1, k)
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double Lm = 0.0, Hm = 0.0;
+          bool any = !MASK;
+          for (int i = 0; i < M; ++i) {
+            if (MASK && P.mask[i][k]) any = true;
+            Lm += lam[i * D + k];
+            Hm += lmu[i * D + k];
+          }
+          const uint32_t slot = (uint32_t)((dr.level - 1) * D + k);
+          const double g = P.randN ? P.randN[s * P.perN + slot] : philox_normal(P.seed, (uint64_t)s, slot);
+          if (any) {
+            const double cov = 1.0 / Lm;
+            X[k] = cov * Hm + sqrt(cov) * g;
+          } else {
+            X[k] = 0.0;
+          }
+        }
+      }
+
+      Hoist<D, MASK> h;
+      double scale = 1.0;  // normaliser common to the whole level (variant A), for the 1e-99 test
+      if (dr.kind == 0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          h.mu[k] = X[k];
+          h.cadd[k] = 0.0;
+          h.act[k] = MASK ? (P.mask[j][k] && P.other[j][k]) : true;
+        }
+      } else {  // leave-one-out product of the other densities' selected kernels
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double Lm = 0.0, Hm = 0.0;
+          for (int i = 0; i < M; ++i) {
+            if (i == j) continue;
+            Lm += lam[i * D + k];
+            Hm += lmu[i * D + k];
+          }
+          const bool oth = MASK ? (P.other[j][k] != 0) : (M > 1);
+          if (oth) {
+            const double cov = 1.0 / Lm;
+            h.cadd[k] = cov;
+            h.mu[k] = cov * Hm;
+          } else {
+            h.cadd[k] = 0.0;
+            h.mu[k] = 0.0;
+          }
+          h.act[k] = (MASK ? (P.mask[j][k] != 0) : true) && oth;
+        }
+      }
+      if (dr.variant == VAR_A) {
+        double prod = 1.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double c = P.hvar[j][k] + h.cadd[k];
+          h.ich[k] = -0.5 / c;
+          if (!MASK || h.act[k]) prod *= c;
+        }
+        scale = kde_rsqrt(prod);
+      }
+
+      double pT;
+      if (dr.variant == VAR_A)
+        pT = pass1<D, MASK, VAR_A>(dr, h, tab, R, q, ck);
+      else if (dr.variant == VAR_B)
+        pT = pass1<D, MASK, VAR_B>(dr, h, tab, R, q, ck);
+      else
+        pT = pass1<D, MASK, VAR_C>(dr, h, tab, R, q, ck);
+
+      // selectLabelOnLevel: the c-th call of this chain reads randU[(s*perU + c) - 1]
+      int zs = 0;
+      if (dr.n > 1) {
+        const uint32_t c = (uint32_t)(M + di);
+        const double u = P.randU ? P.randU[s * P.perU + c - 1] : philox_uniform(P.seed, (uint64_t)s, c);
+        if (pT * scale < 1e-99) {  // :311-315: all p[z] = weight(last node)
+          const double w = dr.wts[dr.n - 1];
+          double tot = 0.0;
+          for (int z = 0; z < dr.n; ++z) tot += w;
+          const double qv = w / tot;
+          double cdf = 0.0;
+          zs = dr.n - 1;
+          bool found = false;
+          for (int z = 0; z < dr.n - 1; ++z) {
+            cdf += qv;
+            if (!found && u <= cdf) {
+              zs = z;
+              found = true;
+            }
+          }
+        } else {
+          const double target = u * pT;
+          int lo = 0, hi = dr.nchunks;  // first chunk whose end-prefix reaches the target
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (target <= ck[mid]) hi = mid; else lo = mid + 1;
+          }
+          if (lo >= dr.nchunks) {
+            zs = dr.n - 1;
+          } else if (dr.G == 1) {
+            zs = lo;
+          } else {
+            const double S0 = lo > 0 ? ck[lo - 1] : 0.0;
+            if (dr.variant == VAR_A)
+              zs = pass2<D, MASK, VAR_A>(dr, h, tab, lo, S0, target);
+            else if (dr.variant == VAR_B)
+              zs = pass2<D, MASK, VAR_B>(dr, h, tab, lo, S0, target);
+            else
+              zs = pass2<D, MASK, VAR_C>(dr, h, tab, lo, S0, target);
+          }
+        }
+      }
+      selpos[j] = zs;
+
+      // updateGlbParticlesVariance!(j)
+      {
+        const double *rs = dr.rec_state + (size_t)zs * dr.state_stride;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          if (MASK && !P.mask[j][k]) {
+            lam[j * D + k] = 0.0;
+            lmu[j * D + k] = 0.0;
+          } else {
+            const double var = dr.state_has_bw ? rs[D + k] : P.hvar[j][k];
+            const double l = 1.0 / var;
+            lam[j * D + k] = l;
+            lmu[j * D + k] = rs[k] * l;
+          }
+        }
+      }
+    }
+
+    // labels (:612-616) and the final samplePoint! (:625)
+    if (live) {
+      const int64_t o = s - P.s0;
+      for (int j = 0; j < M; ++j) P.indices[o * M + j] = P.labels[j][selpos[j]];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double Lm = 0.0, Hm = 0.0;
+        bool any = !MASK;
+        for (int i = 0; i < M; ++i) {
+          if (MASK && P.mask[i][k]) any = true;
+          Lm += lam[i * D + k];
+          Hm += lmu[i * D + k];
+        }
+        double v = 0.0;
+        if (any) {
+          const double cov = 1.0 / Lm;
+          v = cov * Hm;
+          if (P.add_entropy) {
+            const uint32_t slot = (uint32_t)(P.L * D + k);
+            const double g = P.randN ? P.randN[s * P.perN + slot] : philox_normal(P.seed, (uint64_t)s, slot);
+            v = v + sqrt(cov) * g;
+          }
+        }
+        P.points[o * D + k] = v;
+      }
+    }
+  }
+}
+
+template <int D>
+cudaError_t launch_gibbs_d(const GibbsParams &P, bool masked, int grid_cap, size_t smem, cudaStream_t st,
+                                  int sm_count) {
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GB_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int grid = per_sm * sm_count;
+    if (grid > grid_cap) grid = grid_cap;
+    kern<<<grid, GB_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+  };
+  return masked ? launch(gibbs_kernel<D, true>) : launch(gibbs_kernel<D, false>);
+}
+
+
+}  // namespace kdeb200
