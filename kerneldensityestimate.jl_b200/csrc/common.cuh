@@ -142,8 +142,9 @@ __device__ __forceinline__ double kde_exp_flush(double x, const double *__restri
 #endif
 }
 
-__device__ __forceinline__ bool kde_exp_out_of_range(double x) {
-  return (unsigned)(__double2hiint(x) & 0x7FFFFFFF) > 0x4085E000u;
+// x < -700 (or negative NaN) for arguments that are never positive: one unsigned compare
+__device__ __forceinline__ bool kde_exp_below_range(double x) {
+  return (unsigned)__double2hiint(x) > 0xC085E000u;
 }
 
 // reciprocal / reciprocal square root of a normal, positive double without the libdevice

@@ -60,6 +60,26 @@ __device__ __forceinline__ double quad(const double (&x)[D], const double (&r)[S
   return acc;
 }
 
+// Rows whose fast-path total is below EV_TINY (density < 1e-275: the point is > 35 bandwidths away from
+// every component) are recomputed here with libdevice exp, sequentially in leaf order, so that
+// subnormal values and exact zeros (the likelihood's zero rule) match the reference.
+constexpr double EV_TINY = 1e-275;
+__device__ __noinline__ double exact_row(const double *__restrict__ comps, int SE, int D, int64_t N,
+                                         const double *__restrict__ xq, const double *__restrict__ ich, int64_t self) {
+  double s = 0.0;
+  for (int64_t i = 0; i < N; ++i) {
+    if (i == self) continue;
+    const double *r = comps + i * SE;
+    double acc = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double df = __dadd_rn(xq[k], -r[k]);
+      acc = __fma_rn(__dmul_rn(df, df), ich[k], acc);
+    }
+    s = __fma_rn(exp(acc), r[D], s);
+  }
+  return s;
+}
+
 template <int D, int Q, bool LOO>
 __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant__ EvalParams P) {
   constexpr int SE = Rec<D>::SE;
@@ -122,26 +142,18 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
     const double *rec = tiles + (size_t)(t % EV_STAGES) * (EV_TILE_BYTES / 8);
     const bool check = LOO && (a < qhi) && (a + cnt > qlo);
     if (!check) {
+      // branch-free exp for every pair, 2 records x Q queries per iteration (independent chains in one basic
+      // block).  Exponents below -700 are clamped (terms <= 1e-304); rows whose total ends up below
+      // EV_TINY are recomputed exactly at the end, so this never shows in a result.
       int c = 0;
-      for (; c + 2 <= cnt; c += 2) {  // 2 records x Q queries = independent exp chains in one basic block
-        double ra[SE], rb[SE], e[2][Q], a[2][Q];
+      for (; c + 2 <= cnt; c += 2) {
+        double ra[SE], rb[SE], e[2][Q];
         load_rec<SE>(rec + c * SE, ra);
         load_rec<SE>(rec + (c + 1) * SE, rb);
-        bool bad = false;
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
-          a[0][i] = quad<D>(x[i], ra, ich);
-          a[1][i] = quad<D>(x[i], rb, ich);
-          e[0][i] = kde_exp_core(a[0][i], tab);
-          e[1][i] = kde_exp_core(a[1][i], tab);
-          bad = bad || kde_exp_out_of_range(a[0][i]) || kde_exp_out_of_range(a[1][i]);
-        }
-        if (bad) {  // far tails: results near the subnormal range take the IEEE-exact libdevice path
-#pragma unroll
-          for (int i = 0; i < Q; ++i) {
-            e[0][i] = exp(a[0][i]);
-            e[1][i] = exp(a[1][i]);
-          }
+          e[0][i] = kde_exp_flush(quad<D>(x[i], ra, ich), tab);
+          e[1][i] = kde_exp_flush(quad<D>(x[i], rb, ich), tab);
         }
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
@@ -153,11 +165,7 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
         double ra[SE];
         load_rec<SE>(rec + c * SE, ra);
 #pragma unroll
-        for (int i = 0; i < Q; ++i) {
-          const double a = quad<D>(x[i], ra, ich);
-          const double e = kde_exp_out_of_range(a) ? exp(a) : kde_exp_core(a, tab);
-          sum[i] = __fma_rn(e, ra[D], sum[i]);
-        }
+        for (int i = 0; i < Q; ++i) sum[i] = __fma_rn(kde_exp_flush(quad<D>(x[i], ra, ich), tab), ra[D], sum[i]);
       }
     } else {
       for (int c = 0; c < cnt; ++c) {
@@ -165,8 +173,7 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
         load_rec<SE>(rec + c * SE, ra);
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
-          const double a2 = quad<D>(x[i], ra, ich);
-          const double e = kde_exp_out_of_range(a2) ? exp(a2) : kde_exp_core(a2, tab);
+          const double e = kde_exp_flush(quad<D>(x[i], ra, ich), tab);
           if (a + c != self[i]) sum[i] = __fma_rn(e, ra[D], sum[i]);  // leave-one-out (src/DualTree01.jl:146)
         }
       }
@@ -182,7 +189,10 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
     if (P.S > 1) {
       P.partial[(int64_t)blockIdx.y * P.M + qi] = sum[i];
     } else {
-      double v = 0.5 * (sum[i] + sum[i]) / P.norm;  // 0.5*(pMin+pMax)/norm, :335-339
+      double sv = sum[i];
+      if (sv < EV_TINY)
+        sv = exact_row(P.comps, SE, D, P.N, P.queries + (P.q0 + qi) * (int64_t)P.qstride, P.ich, LOO ? P.q0 + qi : -1);
+      double v = 0.5 * (sv + sv) / P.norm;  // 0.5*(pMin+pMax)/norm, :335-339
       if (LOO) v = v / (1.0 - P.comps[(P.q0 + qi) * SE + D]);
       const int64_t o = (LOO && P.perm) ? P.perm[P.q0 + qi] : qi;
       P.out[o] = v;
@@ -192,11 +202,13 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
 
 // sums the S partials of each query in split order and applies the epilogue
 __global__ void eval_finalize_kernel(const double *partial, int S, int64_t M, int64_t q0, const double *comps, int SE,
-                                     int D, double norm, int loo, const int64_t *perm, double *out) {
+                                     int D, int64_t N, const double *queries, int qstride, EvalParams P, double norm,
+                                     int loo, const int64_t *perm, double *out) {
   const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= M) return;
   double s = 0.0;
   for (int y = 0; y < S; ++y) s += partial[(int64_t)y * M + qi];
+  if (s < EV_TINY) s = exact_row(comps, SE, D, N, queries + (q0 + qi) * (int64_t)qstride, P.ich, loo ? q0 + qi : -1);
   double v = 0.5 * (s + s) / norm;
   if (loo) v = v / (1.0 - comps[(q0 + qi) * SE + D]);
   const int64_t o = (loo && perm) ? perm[q0 + qi] : qi;
@@ -313,7 +325,8 @@ int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int6
   if (launches) *launches += 1;
   if (S > 1) {
     eval_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(d_partial, (int)S, M, P.q0, bd->d_leaf, SE, d,
-                                                                      norm, loo, P.perm, d_out);
+                                                                      bd->N, P.queries, P.qstride, P, norm, loo,
+                                                                      P.perm, d_out);
     KDE_CUDA(cudaGetLastError());
     KDE_CUDA(cudaFreeAsync(d_partial, st));
     if (launches) *launches += 1;
