@@ -39,7 +39,7 @@ rows = list(csv.reader(io.StringIO(src)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
 if hi:
     h = rows[hi[0]]
-    data = [r for r in rows[hi[0] + 1:] if len(r) == len(h)]
+    data = [r for r in rows[hi[0] + 1:(hi[1] - 1 if len(hi) > 1 else None)] if len(r) == len(h)]
     ia, isrc = h.index("Instructions Executed"), h.index("Source")
     ops = collections.Counter()
     tot = 0
