@@ -238,7 +238,7 @@ def main():
         a.record()
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(L.kdeb200_gibbs_device(handles, NDENS, Np_total, NITER, 1, None, None, 0, None, 0, SEED, s0, s1,
-                                          d_pts.data_ptr(), d_idx.data_ptr(), st))
+                                          d_pts.data_ptr(), d_idx.data_ptr(), None, st))
         b.record()
         torch.cuda.synchronize()
         kms.append(a.elapsed_time(b))

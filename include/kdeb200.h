@@ -78,15 +78,19 @@ int kdeb200_tree_build_host(int d, int64_t N, const double *points, const double
  *   s0, s1    compute samples s in [s0, s1) of the Np-sample run (0-based); outputs hold only
  *             that range: points_out d x (s1-s0), indices_out ndens x (s1-s0) (= permutation + 1,
  *             the reference's label convention, :612-616).
+ *   level_labels_out  optional (NULL = off): glbs.recordChoosen / labelsChoosen[sample][density][level]
+ *             (:29-31,109-112) as int64 [(s1-s0)][ndens][Nlevels]: permutation of the node selected by
+ *             the last sampleIndex call of each level (0 for internal nodes, -1 if Niter == 0).
  */
 int kdeb200_gibbs(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
                   const uint8_t *dimmask, const double *randU, int64_t nU, const double *randN, int64_t nN,
-                  uint64_t seed, int64_t s0, int64_t s1, double *points_out, int64_t *indices_out);
+                  uint64_t seed, int64_t s0, int64_t s1, double *points_out, int64_t *indices_out,
+                  int64_t *level_labels_out);
 /* Same, outputs (and the optional injected streams) in device memory, asynchronous on `stream`. */
 int kdeb200_gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
                          const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN,
                          int64_t nN, uint64_t seed, int64_t s0, int64_t s1, double *d_points,
-                         int64_t *d_indices, void *stream);
+                         int64_t *d_indices, int64_t *d_level_labels, void *stream);
 /* glbs.Nlevels (src/MSGibbs01.jl:555-568) and the per-sample stream consumption. */
 int kdeb200_gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels,
                         int64_t *uniforms_per_sample, int64_t *normals_per_sample,

@@ -67,9 +67,9 @@ function gibbs1!(Ndens::Int, trees::Vector{BallTreeDensity}, Np::Int, Niter::Int
   GC.@preserve dts hs mask randU randN pts ind begin
     check(ccall((:kdeb200_gibbs, LIB), Cint,
                 (Ptr{Ptr{Cvoid}}, Cint, Int64, Cint, Cint, Ptr{UInt8}, Ptr{Float64}, Int64, Ptr{Float64}, Int64,
-                 UInt64, Int64, Int64, Ptr{Float64}, Ptr{Int64}),
+                 UInt64, Int64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
                 hs, Ndens, Np, Niter, addEntropy, mask, uptr, randU === nothing ? 0 : length(randU),
-                nptr, randN === nothing ? 0 : length(randN), seed, 0, Np, pts, ind))
+                nptr, randN === nothing ? 0 : length(randN), seed, 0, Np, pts, ind, C_NULL))
   end
   nothing
 end

@@ -438,14 +438,15 @@ def philox_streams(seed, Np, perU, perN):
 
 def prodAppxMSGibbsS(npd0, trees, anFcns=None, anParams=None, Niter=3, addop=None, diffop=None, getMu=None,
                      getLambda=None, glbs=None, addEntropy=True, ndims=None, Ndens=None, Np=None, randU=None,
-                     randN=None, partialDimMask=None, seed=None, s0=0, s1=None):
+                     randN=None, partialDimMask=None, seed=None, s0=0, s1=None, recordLabels=False):
     """prodAppxMSGibbsS(npd0, trees, anFcns, anParams; Niter=3, ...) (src/MSGibbs01.jl:645-703).
 
     Returns (points d x Np, indices Ndens x Np) with indices = permutation + 1 (the reference's
     label convention, :612-616).  randU / randN inject the random streams exactly like the
     reference's keyword arguments; without them the kernel draws from Philox4x32-10(seed).
     s0, s1 restrict the call to samples [s0, s1) of the Np-sample run (multi-GPU sharding); the
-    returned arrays then hold only that range."""
+    returned arrays then hold only that range.  recordLabels=True (the reference's
+    glbs.recordChoosen) adds a third result: labelsChoosen as an int64 array [n, Ndens, Nlevels]."""
     _require_euclidean(addop=addop, diffop=diffop, getMu=getMu, getLambda=getLambda)
     trees = list(trees)
     M = len(trees) if Ndens is None else int(Ndens)
@@ -474,10 +475,15 @@ def prodAppxMSGibbsS(npd0, trees, anFcns=None, anParams=None, Niter=3, addop=Non
         seed = int.from_bytes(os.urandom(8), "little")
     points = np.zeros((n, d))
     indices = np.ones((n, M), dtype=np.int64)
+    rec = None
+    if recordLabels:
+        rec = np.zeros((n, M, gibbs_sizes(trees, Niter)[0]), dtype=np.int64)
     check(lib().kdeb200_gibbs(_handles(trees), M, Np, int(Niter), int(bool(addEntropy)),
                               None if mask is None else mask.ctypes.data_as(_lib.u8p), fptr(randU),
                               0 if randU is None else randU.size, fptr(randN), 0 if randN is None else randN.size,
-                              int(seed) & 0xFFFFFFFFFFFFFFFF, int(s0), s1, fptr(points), iptr(indices)))
+                              int(seed) & 0xFFFFFFFFFFFFFFFF, int(s0), s1, fptr(points), iptr(indices), iptr(rec)))
+    if recordLabels:
+        return points.T, indices.T, rec
     return points.T, indices.T
 
 

@@ -24,8 +24,8 @@ int gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels,
                 int64_t *evals);
 int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
                  const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN, int64_t nN,
-                 uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices, cudaStream_t st,
-                 int *launches);
+                 uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices,
+                 int64_t *d_level_labels, cudaStream_t st, int *launches);
 int philox_streams_device(uint64_t seed, int64_t Np, int64_t perU, int64_t perN, double *d_U, double *d_G,
                           cudaStream_t st);
 int pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms_out);
@@ -102,19 +102,21 @@ int kdeb200_gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *
 
 int kdeb200_gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
                          const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN, int64_t nN,
-                         uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices, void *stream) {
+                         uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices,
+                         int64_t *d_level_labels, void *stream) {
   if (int rc = ensure_init()) return rc;
   if (!trees || !d_points || !d_indices) KDE_FAIL(2, "gibbs_device: NULL argument");
   int launches = 0;
   int rc = gibbs_device(trees, ndens, Np, Niter, add_entropy, dimmask, d_randU, nU, d_randN, nN, seed, s0, s1,
-                        d_points, d_indices, (cudaStream_t)stream, &launches);
+                        d_points, d_indices, d_level_labels, (cudaStream_t)stream, &launches);
   ctx().last_launches = launches;
   return rc;
 }
 
 int kdeb200_gibbs(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
                   const uint8_t *dimmask, const double *randU, int64_t nU, const double *randN, int64_t nN,
-                  uint64_t seed, int64_t s0, int64_t s1, double *points_out, int64_t *indices_out) {
+                  uint64_t seed, int64_t s0, int64_t s1, double *points_out, int64_t *indices_out,
+                  int64_t *level_labels_out) {
   if (int rc = ensure_init()) return rc;
   if (!trees || !points_out || !indices_out) KDE_FAIL(2, "gibbs: NULL argument");
   Context &c = ctx();
@@ -141,22 +143,32 @@ int kdeb200_gibbs(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter,
   }
   KDE_CUDA(dP.alloc(sizeof(double) * d * n));
   KDE_CUDA(dI.alloc(sizeof(int64_t) * ndens * n));
+  DevBuf dR(c.stream);
+  int64_t *d_rec = nullptr;
+  if (level_labels_out) {  // never-written entries (Niter == 0) stay -1
+    KDE_CUDA(dR.alloc(sizeof(int64_t) * ndens * n * L));
+    KDE_CUDA(cudaMemsetAsync(dR.p, 0xFF, sizeof(int64_t) * ndens * n * L, c.stream));
+    d_rec = dR.as<int64_t>();
+  }
   Timer tm(c);
   int launches = 0;
   int rc;
   if (randU) {
     // device slices are re-based: sample s reads U[(s-s0)*perU + c - 1 + 1] => pass pointer + 1
     rc = gibbs_device(trees, ndens, n, Niter, add_entropy, dimmask, dU.as<double>() + 1, n * perU - 1,
-                      dN.as<double>(), n * perN, seed, 0, n, dP.as<double>(), dI.as<int64_t>(), c.stream, &launches);
+                      dN.as<double>(), n * perN, seed, 0, n, dP.as<double>(), dI.as<int64_t>(), d_rec, c.stream,
+                      &launches);
   } else {
     rc = gibbs_device(trees, ndens, Np, Niter, add_entropy, dimmask, nullptr, 0, nullptr, 0, seed, s0, s1,
-                      dP.as<double>(), dI.as<int64_t>(), c.stream, &launches);
+                      dP.as<double>(), dI.as<int64_t>(), d_rec, c.stream, &launches);
   }
   if (rc) return rc;
   tm.stop();
   c.last_launches = launches;
   KDE_CUDA(cudaMemcpyAsync(points_out, dP.p, sizeof(double) * d * n, cudaMemcpyDeviceToHost, c.stream));
   KDE_CUDA(cudaMemcpyAsync(indices_out, dI.p, sizeof(int64_t) * ndens * n, cudaMemcpyDeviceToHost, c.stream));
+  if (level_labels_out)
+    KDE_CUDA(cudaMemcpyAsync(level_labels_out, dR.p, sizeof(int64_t) * ndens * n * L, cudaMemcpyDeviceToHost, c.stream));
   KDE_CUDA(cudaStreamSynchronize(c.stream));
   return 0;
 }

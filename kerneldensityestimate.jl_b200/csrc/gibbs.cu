@@ -56,6 +56,7 @@ static void build_schedule(const kdeb200_tree_t *trees, int M, int L, int T, boo
         dr.new_level = (pass == 0 && j == 0) ? 1 : 0;
         dr.n = (int)lv.n;
         dr.wts = t->d_buf + lv.offW;
+        dr.levperm = t->d_levperm + lv.offP;
         if (lv.cls == 0) {
           dr.variant = VAR_A;
           dr.rec = t->d_buf + lv.offA;
@@ -119,8 +120,8 @@ int gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels,
 
 int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
                  const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN, int64_t nN,
-                 uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices, cudaStream_t st,
-                 int *launches) {
+                 uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices,
+                 int64_t *d_level_labels, cudaStream_t st, int *launches) {
   Context &c = ctx();
   int L = 0;
   int64_t perU = 0, perN = 0;
@@ -170,6 +171,7 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
   P.randN = d_randN;
   P.points = d_points;
   P.indices = d_indices;
+  P.level_labels = d_level_labels;
   P.s0 = s0;
   P.s1 = s1;
   P.perU = perU;

@@ -47,6 +47,7 @@ struct alignas(16) Draw {
   const double *rec;        // evaluation records of this level (variant-specific layout)
   const double *rec_state;  // records the chain state is refreshed from ([m.., lnw] or [m.., b.., lnw])
   const double *wts;        // raw weights (fallback path)
+  const int64_t *levperm;   // permutation of the level's nodes (label recording)
   int n;                    // nodes on the level
   int stride;               // doubles per evaluation record
   int state_stride;
@@ -76,6 +77,7 @@ struct GibbsParams {
   const double *randU, *randN;  // injected streams or null (Philox)
   double *points;               // d x (s1-s0)
   int64_t *indices;             // M x (s1-s0)
+  int64_t *level_labels;        // optional [(s1-s0)][M][L]: labelsChoosen (src/MSGibbs01.jl:109-112)
   int64_t s0, s1, perU, perN;
   uint64_t seed;
   int ndraws, ntiles, M, L, T, add_entropy, nbatches;
@@ -473,6 +475,8 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
         }
       }
       selpos[j] = zs;
+      if (P.level_labels && dr.kind == 1 && live)  // sampleIndex records permutation[ind[j]] per (sample, density, level)
+        P.level_labels[((s - P.s0) * M + j) * P.L + (dr.level - 1)] = dr.levperm[zs];
 
       // updateGlbParticlesVariance!(j)
       {

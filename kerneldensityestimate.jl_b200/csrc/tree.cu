@@ -292,12 +292,18 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
     }
   }
   for (size_t z = 0; z < lab.size(); ++z) lab[z] = perm[lists.back()[z] - 1] + 1;
+  std::vector<int64_t> levperm;
+  for (size_t l = 0; l < lists.size(); ++l) {
+    t->levels[l].offP = (int64_t)levperm.size();
+    for (int64_t y : lists[l]) levperm.push_back(perm[y - 1]);
+  }
 
   Context &c = ctx();
   auto fail = [&](cudaError_t e, const char *what) {
     set_error("tree_create: %s: %s", what, cudaGetErrorString(e));
     if (t->d_buf) cudaFree(t->d_buf);
     if (t->d_labels) cudaFree(t->d_labels);
+    if (t->d_levperm) cudaFree(t->d_levperm);
     if (t->d_leaf) cudaFree(t->d_leaf);
     if (t->d_perm) cudaFree(t->d_perm);
     delete t;
@@ -306,14 +312,16 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
   cudaError_t e;
   if ((e = cudaMalloc(&t->d_buf, sizeof(double) * h.size())) != cudaSuccess) return fail(e, "cudaMalloc records");
   if ((e = cudaMalloc(&t->d_labels, sizeof(int64_t) * lab.size())) != cudaSuccess) return fail(e, "cudaMalloc labels");
+  if ((e = cudaMalloc(&t->d_levperm, sizeof(int64_t) * levperm.size())) != cudaSuccess) return fail(e, "cudaMalloc levperm");
   if ((e = cudaMalloc(&t->d_leaf, sizeof(double) * leaf.size())) != cudaSuccess) return fail(e, "cudaMalloc leaves");
   if ((e = cudaMalloc(&t->d_perm, sizeof(int64_t) * pr.size())) != cudaSuccess) return fail(e, "cudaMalloc perm");
   if ((e = cudaMemcpyAsync(t->d_buf, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return fail(e, "H2D records");
   if ((e = cudaMemcpyAsync(t->d_labels, lab.data(), sizeof(int64_t) * lab.size(), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return fail(e, "H2D labels");
+  if ((e = cudaMemcpyAsync(t->d_levperm, levperm.data(), sizeof(int64_t) * levperm.size(), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return fail(e, "H2D levperm");
   if ((e = cudaMemcpyAsync(t->d_leaf, leaf.data(), sizeof(double) * leaf.size(), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return fail(e, "H2D leaves");
   if ((e = cudaMemcpyAsync(t->d_perm, pr.data(), sizeof(int64_t) * pr.size(), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return fail(e, "H2D perm");
   if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return fail(e, "sync");  // host vectors die here
-  t->device_bytes = sizeof(double) * (h.size() + leaf.size()) + sizeof(int64_t) * (lab.size() + pr.size());
+  t->device_bytes = sizeof(double) * (h.size() + leaf.size()) + sizeof(int64_t) * (lab.size() + pr.size() + levperm.size());
   *out = t;
   return 0;
 }
@@ -322,6 +330,7 @@ int tree_destroy(kdeb200_tree_t t) {
   if (!t) return 0;
   cudaFree(t->d_buf);
   cudaFree(t->d_labels);
+  cudaFree(t->d_levperm);
   cudaFree(t->d_leaf);
   cudaFree(t->d_perm);
   if (t->d_leaf32) cudaFree(t->d_leaf32);

@@ -16,6 +16,7 @@ struct Level {
   int64_t offA = -1;  // cls 0: records [m_0..m_{d-1}, ln w]            stride SA
   int64_t offB = -1;  // cls 1: records [m_k.., -0.5/b_k.., ln w - 0.5 sum ln b_k]   stride SC
   int64_t offC = -1;  // cls 1: records [m_k.., b_k.., ln w]            stride SC
+  int64_t offP = 0;   // permutation of the level's nodes (0 for internal nodes), in d_levperm
 };
 
 }  // namespace kdeb200
@@ -32,6 +33,7 @@ struct kdeb200_tree_s {
   double *d_buf = nullptr;             // all level records
   size_t buf_doubles = 0;
   int64_t *d_labels = nullptr;  // deepest level, level order: permutation + 1 (src/MSGibbs01.jl:615)
+  int64_t *d_levperm = nullptr; // every level, level order: permutation (labelsChoosen, src/MSGibbs01.jl:111)
   double *d_leaf = nullptr;     // leaf order (N+1..2N): [x_0..x_{d-1}, w], stride SE -- evalDirect's order
   int64_t *d_perm = nullptr;    // leaf order: original 0-based index
   float *d_leaf32 = nullptr;    // lazily built FP32 shadow of d_leaf (centred, pre-scaled), eval_f32.cu

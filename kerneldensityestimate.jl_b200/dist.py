@@ -95,7 +95,7 @@ def prod_sharded_device(handles, ndens, dims, Np_total, Niter, seed, d_points, d
     s0, s1 = shard_range(Np_total, rank, world)
     st = torch.cuda.current_stream().cuda_stream if stream is None else stream
     _lib.check(_lib.lib().kdeb200_gibbs_device(handles, ndens, Np_total, Niter, 1, None, None, 0, None, 0, seed, s0,
-                                               s1, d_points.data_ptr(), d_indices.data_ptr(), st))
+                                               s1, d_points.data_ptr(), d_indices.data_ptr(), None, st))
     if world > 1:
         dist.all_gather_into_tensor(g_points, d_points, group=group)
         dist.all_gather_into_tensor(g_indices, d_indices, group=group)

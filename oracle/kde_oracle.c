@@ -581,6 +581,7 @@ typedef struct {
   double mn, vn;
   double *calclambdas, *calcmu;
   const uint8_t *mask; /* mask[j*Ndim + k], NULL = all active */
+  int64_t *record;     /* labelsChoosen[s][j][level] flattened [Np][Ndens][Nlevels], or NULL */
 } gbglb;
 
 #define LL(g, j, z) ((g)->levelList[((z)-1) * (g)->Ndens + ((j)-1)])
@@ -592,8 +593,10 @@ static int mask_on(const gbglb *g, int64_t j, int64_t dim) {
   return g->mask ? (g->mask[(j - 1) * g->Ndim + (dim - 1)] != 0) : 1;
 }
 
-/* updateGlbParticlesVariance! (src/MSGibbs01.jl:89-115) */
-static void update_particles_variance(gbglb *g, int64_t j) {
+/* updateGlbParticlesVariance! (src/MSGibbs01.jl:89-115); idx/level > 0 <=> recordChoosen (:109-112) */
+static void update_particles_variance_rec(gbglb *g, int64_t j, int64_t idx, int64_t level);
+static void update_particles_variance(gbglb *g, int64_t j) { update_particles_variance_rec(g, j, 0, 0); }
+static void update_particles_variance_rec(gbglb *g, int64_t j, int64_t idx, int64_t level) {
   for (int64_t dim = 1; dim <= g->Ndim; ++dim) {
     if (!mask_on(g, j, dim)) {
       PART(g, dim, j) = 0.0;
@@ -603,6 +606,8 @@ static void update_particles_variance(gbglb *g, int64_t j) {
       VARI(g, dim, j) = BWD(g->trees[j - 1], g->ind[j - 1], dim);
     }
   }
+  if (g->record && idx > 0)
+    g->record[((idx - 1) * g->Ndens + (j - 1)) * g->Nlevels + (level - 1)] = PERM(g->trees[j - 1], g->ind[j - 1]);
 }
 
 /* calcIndices! (src/MSGibbs01.jl:123-130) */
@@ -700,12 +705,12 @@ static void sample_indices(gbglb *g, int64_t offset) {
 }
 
 /* sampleIndex (src/MSGibbs01.jl:404-429) */
-static void sample_index(int64_t j, gbglb *g) {
+static void sample_index(int64_t j, gbglb *g, int64_t idx, int64_t level) {
   for (int64_t i = 1; i <= g->Ndim; ++i)
     gaussian_product_mean_cov(g, i, &g->Malmost[i - 1], &g->Calmost[i - 1], j);
   make_faster_sample_index(j, g, g->Malmost, g->Calmost, 0, 1);
   select_label_on_level(g, j);
-  update_particles_variance(g, j);
+  update_particles_variance_rec(g, j, idx, level);
 }
 
 /* samplePoint! (src/MSGibbs01.jl:440-463) */
@@ -774,9 +779,20 @@ int64_t okde_gibbs_nlevels(const okde *const *trees, int64_t ndens) {
  * the stream pointers advance by a constant per sample (Ndens*(1+L*(1+Niter)) uniforms,
  * Ndim*(L+1) normals -- verified against the sequential run in tests/), so starting at s0
  * just offsets them. */
+int okde_gibbs_record(int64_t ndens, const okde *const *trees, int64_t Np, int64_t Niter, double *pts,
+                      int64_t *ind, const double *randU, int64_t nU, const double *randN, int64_t nN,
+                      int add_entropy, const uint8_t *mask, int64_t s0, int64_t s1, int64_t *record);
+
 int okde_gibbs(int64_t ndens, const okde *const *trees, int64_t Np, int64_t Niter, double *pts, int64_t *ind,
                const double *randU, int64_t nU, const double *randN, int64_t nN, int add_entropy,
                const uint8_t *mask, int64_t s0, int64_t s1) {
+  return okde_gibbs_record(ndens, trees, Np, Niter, pts, ind, randU, nU, randN, nN, add_entropy, mask, s0, s1, NULL);
+}
+
+/* record: labelsChoosen (glbs.recordChoosen = true), [Np][ndens][Nlevels], entries never written stay untouched */
+int okde_gibbs_record(int64_t ndens, const okde *const *trees, int64_t Np, int64_t Niter, double *pts,
+                      int64_t *ind, const double *randU, int64_t nU, const double *randN, int64_t nN,
+                      int add_entropy, const uint8_t *mask, int64_t s0, int64_t s1, int64_t *record) {
   gbglb G;
   gbglb *g = &G;
   memset(g, 0, sizeof(G));
@@ -786,6 +802,7 @@ int okde_gibbs(int64_t ndens, const okde *const *trees, int64_t Np, int64_t Nite
   g->randU = randU;
   g->randN = randN;
   g->mask = mask;
+  g->record = record;
   g->Ndim = 0;
   int64_t maxNp = 0;
   for (int64_t j = 0; j < ndens; ++j) {
@@ -827,7 +844,7 @@ int okde_gibbs(int64_t ndens, const okde *const *trees, int64_t Np, int64_t Nite
       level_down(g);
       sample_indices(g, frm);
       for (int64_t i = 1; i <= Niter; ++i)
-        for (int64_t j = 1; j <= ndens; ++j) sample_index(j, g);
+        for (int64_t j = 1; j <= ndens; ++j) sample_index(j, g, s, l);
     }
     for (int64_t j = 1; j <= ndens; ++j) /* :612-616, the "+1" quirk */
       ind[(s - 1) * ndens + (j - 1)] = PERM(trees[j - 1], g->ind[j - 1]) + 1;

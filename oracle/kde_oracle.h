@@ -69,6 +69,11 @@ int okde_gibbs(int64_t ndens, const okde *const *trees, int64_t Np, int64_t Nite
                const uint8_t *mask /* ndens*d bytes (1 = active) or NULL */,
                int64_t s0, int64_t s1);
 
+/* same with labelsChoosen recording (src/MSGibbs01.jl:109-112): record[(s*ndens + j)*Nlevels + (l-1)] */
+int okde_gibbs_record(int64_t ndens, const okde *const *trees, int64_t Np, int64_t Niter, double *pts,
+                      int64_t *ind, const double *randU, int64_t nU, const double *randN, int64_t nN,
+                      int add_entropy, const uint8_t *mask, int64_t s0, int64_t s1, int64_t *record);
+
 /* bounded-sample timing helpers for the CPU baseline (OpenMP over independent rows/chains) */
 int okde_gibbs_omp(int64_t ndens, const okde *const *trees, int64_t Np, int64_t Niter,
                    double *pts, int64_t *ind, const double *randU, int64_t nU,

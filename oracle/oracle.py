@@ -65,6 +65,7 @@ def lib():
         L.okde_gibbs_nlevels.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
         L.okde_gibbs.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_int64, C.c_int64, f64p, i64p, f64p,
                                  C.c_int64, f64p, C.c_int64, C.c_int, u8p, C.c_int64, C.c_int64]
+        L.okde_gibbs_record.argtypes = L.okde_gibbs.argtypes + [i64p]
         L.okde_gibbs_omp.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_int64, C.c_int64, f64p, i64p, f64p,
                                      C.c_int64, f64p, C.c_int64, C.c_int, u8p, C.c_int]
         L.okde_max_threads.restype = C.c_int
@@ -213,8 +214,9 @@ def gibbs_nlevels(trees):
     return lib().okde_gibbs_nlevels(arr, len(trees))
 
 
-def gibbs(trees, Np, Niter, randU, randN, add_entropy=True, mask=None, s0=0, s1=None, nthreads=0):
-    """gibbs1 with injected random streams.  Returns (points d x Np, indices M x Np)."""
+def gibbs(trees, Np, Niter, randU, randN, add_entropy=True, mask=None, s0=0, s1=None, nthreads=0, record=False):
+    """gibbs1 with injected random streams.  Returns (points d x Np, indices M x Np) and, with
+    record=True, labelsChoosen as an int64 array [Np, M, Nlevels] (-1 = never written)."""
     M = len(trees)
     d = max(t.dims for t in trees)
     arr = (C.c_void_p * M)(*[t.ptr for t in trees])
@@ -226,6 +228,13 @@ def gibbs(trees, Np, Niter, randU, randN, add_entropy=True, mask=None, s0=0, s1=
     if mask is not None:
         mk = np.ascontiguousarray(np.asarray(mask, dtype=np.uint8).reshape(M, d))
     mp = None if mk is None else mk.ctypes.data_as(u8p)
+    if record:
+        rec = np.full((Np, M, gibbs_nlevels(trees)), -1, dtype=np.int64)
+        rc = lib().okde_gibbs_record(M, arr, Np, Niter, _f(pts), _i(ind), _f(randU), randU.size, _f(randN), randN.size,
+                                     int(bool(add_entropy)), mp, s0, Np if s1 is None else s1, _i(rec))
+        if rc:
+            raise RuntimeError("oracle gibbs failed rc=%d" % rc)
+        return pts, ind, rec
     if nthreads:
         rc = lib().okde_gibbs_omp(M, arr, Np, Niter, _f(pts), _i(ind), _f(randU), randU.size, _f(randN), randN.size,
                                   int(bool(add_entropy)), mp, int(nthreads))

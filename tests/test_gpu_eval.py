@@ -120,3 +120,25 @@ def test_fp32_variant_within_1e5(d, N, M):
     got = K.evaluateDualTree(p, pos, precision=K.F32)
     assert relerr(got, exp) < 1e-5
     assert relerr(K.evaluateDualTree(p, p, precision=K.F32), o.evaluate()) < 1e-5
+
+
+def test_full_size_c5_spot_check():
+    """BASELINE config 5 at full size (1M components, 3-D): 256 of the query points against the oracle
+    (1e-12), FP32 variant within 1e-5, plus linearity in the weights (a size-independent property)."""
+    rng = np.random.default_rng(20261017)
+    N = 1_000_000
+    pts = mixture(rng, 3, N)
+    bw = silverman(pts)
+    p = K.kde(pts, bw)
+    pos = mixture(rng, 3, 50_000)
+    got = K.evaluateDualTree(p, pos)
+    o = OKDE.kde_bw(pts, bw)
+    exp = o.evaluate(pos[:, :256], nthreads=8)
+    assert relerr(got[:256], exp) < TOL
+    assert relerr(K.evaluateDualTree(p, pos, precision=K.F32), got) < 1e-5
+    w = rng.random(N) + 0.5
+    pa, pb = K.kde(pts[:, : N // 2], bw, w[: N // 2]), K.kde(pts[:, N // 2:], bw, w[N // 2:])
+    pw = K.kde(pts, bw, w)
+    fa = w[: N // 2].sum() / w.sum()
+    mix = fa * K.evaluateDualTree(pa, pos[:, :2000]) + (1 - fa) * K.evaluateDualTree(pb, pos[:, :2000])
+    assert relerr(K.evaluateDualTree(pw, pos[:, :2000]), mix) < 1e-11

@@ -163,3 +163,45 @@ def test_product_operator_and_errors():
         K.prodAppxMSGibbsS(p, [p, q], None, None, randU=np.zeros(10), randN=np.zeros(10))
     with pytest.raises(K.KDEError):
         K.prodAppxMSGibbsS(p, [p, q], None, None, getMu=(lambda *a: 0,))
+
+
+def test_label_recording_matches_oracle():
+    """glbs.recordChoosen / labelsChoosen[sample][density][level] (src/MSGibbs01.jl:29-31,109-112)."""
+    rng = np.random.default_rng(31)
+    pairs = [make(rng, 2, 37, 0.3 * j) for j in range(3)]
+    kt, ot = [p[0] for p in pairs], [p[1] for p in pairs]
+    Np, T = 150, 4
+    nU, nN = O.prod_sizes(ot, Np, T)
+    U, G = rng.random(nU), rng.standard_normal(nN)
+    ep, ei, er = O.gibbs(ot, Np, T, U, G, record=True)
+    gp, gi, gr = K.prodAppxMSGibbsS(None, kt, None, None, Niter=T, Np=Np, randU=U, randN=G, recordLabels=True)
+    assert gr.shape == er.shape == (Np, 3, O.gibbs_nlevels(ot))
+    assert np.array_equal(gr, er) and np.array_equal(gi, ei)
+    assert np.array_equal(gr[:, :, -1] + 1, gi.T)          # the last level's record is the output label - 1
+    assert (gr[:, :, 0] == 0).all()                        # level 1 nodes are internal: permutation 0
+    _, _, g0 = K.prodAppxMSGibbsS(None, kt, None, None, Niter=0, Np=8, seed=1, recordLabels=True)
+    assert (g0 == -1).all()                                # sampleIndex never ran
+
+
+def test_full_size_c4_properties():
+    """BASELINE config 4 at full size (8 x 4096 components, 3-D, 1M samples, Niter=5): size-independent
+    properties -- determinism, sharding invariance on slices, label range, agreement of the product
+    moments between two independent seeds, and the exact point/label relation with addEntropy=false."""
+    import bench
+    trees = [K.kde(bench.synth_points(j), bench.silverman(bench.synth_points(j))) for j in range(bench.NDENS)]
+    Np = 1_000_000
+    p1, i1 = K.prodAppxMSGibbsS(None, trees, None, None, Niter=5, Np=Np, seed=11)
+    assert p1.shape == (3, Np) and i1.shape == (8, Np) and np.isfinite(p1).all()
+    assert i1.min() >= 2 and i1.max() <= 4097
+    a, ai = K.prodAppxMSGibbsS(None, trees, None, None, Niter=5, Np=Np, seed=11, s0=123_456, s1=125_000)
+    assert np.array_equal(a, p1[:, 123_456:125_000]) and np.array_equal(ai, i1[:, 123_456:125_000])
+    p2, _ = K.prodAppxMSGibbsS(None, trees, None, None, Niter=5, Np=Np, seed=12)
+    se = p1.std(axis=1) / np.sqrt(Np / 50.0)               # generous: chains are independent across samples
+    assert np.all(np.abs(p1.mean(axis=1) - p2.mean(axis=1)) < 6 * se)
+    assert np.all(np.abs(p1.std(axis=1) / p2.std(axis=1) - 1) < 0.02)
+    q, qi = K.prodAppxMSGibbsS(None, trees, None, None, Niter=5, Np=4096, seed=11, addEntropy=False)
+    lam = np.stack([1.0 / (K.getBW(t)[:, 0] ** 2) for t in trees])
+    pts = [K.getPoints(t) for t in trees]
+    for s in range(0, 4096, 97):
+        mus = np.stack([pts[j][:, qi[j, s] - 2] for j in range(8)])
+        assert np.allclose(q[:, s], (lam * mus).sum(0) / lam.sum(0), rtol=1e-12, atol=1e-14)
