@@ -88,36 +88,49 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t sample, 
 }
 
 // ---------------------------------------------------------------- FP64 exp --------------
-#define KDE_EXP_TAB 256
-__constant__ double kExpC[8] = {
-    369.3299304675746,      // 256/ln2
-    6755399441055744.0,      // 1.5 * 2^52: the low word of x*256/ln2 + this is n = rint(x*256/ln2)
-    -0.0027076061740622863,  // -ln2/256 (rounded)
-    -9.058776616587108e-20,  // -(ln2/256 - rounded), from 60-digit ln2
-    4.1666666666666664e-02,  // 1/24
-    1.6666666666666666e-01,  // 1/6
-    0.5,
-    0.0};
+#ifndef KDE_EXP_TAB
+#define KDE_EXP_TAB 2048
+#endif
+#if KDE_EXP_TAB == 2048
+#define KDE_EXP_K 2954.639443740597       /* 2048/ln2 */
+#define KDE_EXP_C1 -0.0003384507717577858   /* -ln2/2048 (rounded) */
+#define KDE_EXP_SHL 9                    /* (n >> 11) << 20 == (n & ~2047) << 9 */
+#elif KDE_EXP_TAB == 256
+#define KDE_EXP_K 369.3299304675746
+#define KDE_EXP_C1 -0.0027076061740622863
+#define KDE_EXP_SHL 12
+#else
+#error "KDE_EXP_TAB must be 256 or 2048"
+#endif
+__constant__ double kExpC[4] = {
+    KDE_EXP_K,           // TAB/ln2
+    6755399441055744.0,  // 1.5 * 2^52: the low word of x*TAB/ln2 + this is n = rint(x*TAB/ln2)
+    KDE_EXP_C1,          // -ln2/TAB (rounded)
+    1.6666666666666666e-01};
 
-// exp(x) = 2^(n >> 8) * T[n & 255] * e^r,  n = rint(x*256/ln2), |r| <= ln2/512: degree-4 Taylor
-// (truncation r^5/120 <= 3.8e-17), 9 FP64-pipe instructions (libdevice exp(): 17) + 4 integer ops + one
-// shared-memory table load; ~1 ulp.  Valid for |x| <= 700 (normal results); anything else must be
-// fixed up by the caller.  Branch-free so that independent evaluations interleave in one basic
-// block; coefficients sit in the constant bank so DFMA reads them as operands.
+// exp(x) = 2^(n / TAB) * e^r = 2^(n >> log2 TAB) * T[n mod TAB] * e^r,  n = rint(x*TAB/ln2), |r| <= ln2/(2 TAB).
+//   TAB = 2048 (16 KB shared memory): degree-3 Taylor (truncation r^4/24 <= 3.4e-17)  -> 7 FP64 instructions
+//   TAB = 256                       : degree-4 Taylor (r^5/120 <= 3.8e-17)            -> 8 FP64 instructions
+// (libdevice exp(): 17) + 5 integer/LDS instructions.  The reduction uses ONE constant: r = x - n*fl(ln2/TAB)
+// is exact up to its own rounding (FMA) and differs from the true remainder by n*(ln2/TAB - fl(.)), a relative
+// error of 3.4e-17*|x| in the result (< 1e-15 for every term that can matter in a sum, 2.4e-14 at the
+// clamp).  Valid for |x| <= 700 (normal results); anything else must be fixed up by the caller.  Branch-free
+// so that independent evaluations interleave in one basic block; constants are constant-bank operands.
 __device__ __forceinline__ double kde_exp_core(double x, const double *__restrict__ tab) {
   const double t = __fma_rn(x, kExpC[0], kExpC[1]);
   const int n = __double2loint(t);
   const double nf = __dadd_rn(t, -kExpC[1]);
-  double r = __fma_rn(nf, kExpC[2], x);
-  r = __fma_rn(nf, kExpC[3], r);
-  double q = __fma_rn(r, kExpC[4], kExpC[5]);
-  q = __fma_rn(q, r, kExpC[6]);
+  const double r = __fma_rn(nf, kExpC[2], x);
   const double r2 = __dmul_rn(r, r);
+#if KDE_EXP_TAB == 2048
+  const double q = __fma_rn(r, kExpC[3], 0.5);
+#else
+  const double q = __fma_rn(__fma_rn(r, 4.1666666666666664e-02, kExpC[3]), r, 0.5);
+#endif
   const double p = __fma_rn(q, r2, r);
   const double T = tab[n & (KDE_EXP_TAB - 1)];
   const double y = __fma_rn(T, p, T);
-  // exponent: (n >> 8) << 20 == (n & ~255) << 12
-  return __hiloint2double(__double2hiint(y) + (n & ~(KDE_EXP_TAB - 1)) * 4096, __double2loint(y));
+  return __hiloint2double(__double2hiint(y) + ((n & ~(KDE_EXP_TAB - 1)) << KDE_EXP_SHL), __double2loint(y));
 }
 
 // Gibbs flavour: x < -700 (p < 1e-304) is clamped (or flushed to 0 with KDE_FLUSH_SELECT), negative NaN -> tiny

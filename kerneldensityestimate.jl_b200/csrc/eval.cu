@@ -254,6 +254,8 @@ static cudaError_t launch_eval_d(const EvalParams &P, dim3 grid, size_t smem, cu
   auto kern = eval_kernel<D, Q, LOO>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   kern<<<grid, EV_THREADS, smem, st>>>(P);
   return cudaGetLastError();
 }

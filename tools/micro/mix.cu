@@ -10,8 +10,8 @@ namespace kdeb200 { void set_error(const char*, ...) {} }
 // VAR: 0 = A (hoisted), 1 = C (per-dim rcp + rsqrt), 2 = C' (one rsqrt of the product, reciprocals by products)
 template <int VAR, int UNR, bool MUFU>
 __global__ void __launch_bounds__(128, 4) k(int iters, const double *in, double *out) {
-  __shared__ double tab[64];
-  if (threadIdx.x < 64) tab[threadIdx.x] = in[threadIdx.x];
+  __shared__ double tab[KDE_EXP_TAB];
+  for (int i = threadIdx.x; i < KDE_EXP_TAB; i += blockDim.x) tab[i] = in[i & 63];
   __syncthreads();
   double mu[3], ich[3], cadd[3];
   for (int k = 0; k < 3; ++k) { mu[k] = in[64 + k] + threadIdx.x * 1e-3; ich[k] = -in[67 + k]; cadd[k] = in[70 + k]; }
