@@ -102,11 +102,16 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t sample, 
 #else
 #error "KDE_EXP_TAB must be 256 or 2048"
 #endif
-__constant__ double kExpC[4] = {
-    KDE_EXP_K,           // TAB/ln2
-    6755399441055744.0,  // 1.5 * 2^52: the low word of x*TAB/ln2 + this is n = rint(x*TAB/ln2)
-    KDE_EXP_C1,          // -ln2/TAB (rounded)
-    1.6666666666666666e-01};
+// The four constants travel in the kernel-parameter struct (ExpConsts) so that ptxas uses them as
+// c[0x0][..] operands: a DFMA with three distinct REGISTER sources issues at 2/3 rate on this part
+// (register-bank limit, tools/micro/ops.cu), one with a constant-bank or immediate operand at full rate.
+struct ExpConsts {
+  double k;      // TAB/ln2
+  double shift;  // 1.5 * 2^52: the low word of x*TAB/ln2 + shift is n = rint(x*TAB/ln2)
+  double c1;     // -ln2/TAB (rounded)
+  double sixth;  // 1/6
+};
+inline ExpConsts make_exp_consts() { return ExpConsts{KDE_EXP_K, 6755399441055744.0, KDE_EXP_C1, 1.6666666666666666e-01}; }
 
 // exp(x) = 2^(n / TAB) * e^r = 2^(n >> log2 TAB) * T[n mod TAB] * e^r,  n = rint(x*TAB/ln2), |r| <= ln2/(2 TAB).
 //   TAB = 2048 (16 KB shared memory): degree-3 Taylor (truncation r^4/24 <= 3.4e-17)  -> 7 FP64 instructions
@@ -115,19 +120,19 @@ __constant__ double kExpC[4] = {
 // is exact up to its own rounding (FMA) and differs from the true remainder by n*(ln2/TAB - fl(.)), a relative
 // error of 3.4e-17*|x| in the result (< 1e-15 for every term that can matter in a sum, 2.4e-14 at the
 // clamp).  Valid for |x| <= 700 (normal results); anything else must be fixed up by the caller.  Branch-free
-// so that independent evaluations interleave in one basic block; constants are constant-bank operands.
-__device__ __forceinline__ double kde_exp_core(double x, const double *__restrict__ tab) {
-  const double t = __fma_rn(x, kExpC[0], kExpC[1]);
+// so that independent evaluations interleave in one basic block.  Every DFMA has at most two distinct
+// register sources: p = r + (q r) r instead of r + q r^2.
+__device__ __forceinline__ double kde_exp_core(double x, const double *__restrict__ tab, const ExpConsts &ec) {
+  const double t = __fma_rn(x, ec.k, 6755399441055744.0);  // 1.5*2^52 has zero low word: an FP64 immediate
   const int n = __double2loint(t);
-  const double nf = __dadd_rn(t, -kExpC[1]);
-  const double r = __fma_rn(nf, kExpC[2], x);
-  const double r2 = __dmul_rn(r, r);
+  const double nf = __dadd_rn(t, -6755399441055744.0);
+  const double r = __fma_rn(nf, ec.c1, x);
 #if KDE_EXP_TAB == 2048
-  const double q = __fma_rn(r, kExpC[3], 0.5);
+  const double q = __fma_rn(r, ec.sixth, 0.5);
 #else
-  const double q = __fma_rn(__fma_rn(r, 4.1666666666666664e-02, kExpC[3]), r, 0.5);
+  const double q = __fma_rn(__fma_rn(r, 4.1666666666666664e-02, ec.sixth), r, 0.5);
 #endif
-  const double p = __fma_rn(q, r2, r);
+  const double p = __fma_rn(__dmul_rn(q, r), r, r);
   const double T = tab[n & (KDE_EXP_TAB - 1)];
   const double y = __fma_rn(T, p, T);
   return __hiloint2double(__double2hiint(y) + ((n & ~(KDE_EXP_TAB - 1)) << KDE_EXP_SHL), __double2loint(y));
@@ -137,9 +142,9 @@ __device__ __forceinline__ double kde_exp_core(double x, const double *__restric
 // (the reference maps NaN weights to 0, src/MSGibbs01.jl:302).  A flushed term can never matter:
 // either pT >= 1e-99 and the term is < 1e-205 of it, or every term is that small and the
 // pT < 1e-99 fallback (:311) fires with or without it.  Integer compares: no FP64-pipe cost.
-__device__ __forceinline__ double kde_exp_flush(double x, const double *__restrict__ tab) {
+__device__ __forceinline__ double kde_exp_flush(double x, const double *__restrict__ tab, const ExpConsts &ec) {
 #ifdef KDE_FLUSH_SELECT
-  const double y = kde_exp_core(x, tab);
+  const double y = kde_exp_core(x, tab, ec);
   const int hx = __double2hiint(x);
   const bool under = (unsigned)hx > 0xC085E000u;
   const bool over = hx > 0x4085E000;
@@ -151,7 +156,7 @@ __device__ __forceinline__ double kde_exp_flush(double x, const double *__restri
   // replaced by ~1e-304, which is equally irrelevant -- see above); x <= 700 is the caller's
   // contract (exponents are ln w plus non-positive terms, plus at most -0.5 sum ln b_k).
   const unsigned hx = min((unsigned)__double2hiint(x), 0xC085E000u);
-  return kde_exp_core(__hiloint2double((int)hx, __double2loint(x)), tab);
+  return kde_exp_core(__hiloint2double((int)hx, __double2loint(x)), tab, ec);
 #endif
 }
 

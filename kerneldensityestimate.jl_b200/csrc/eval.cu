@@ -27,6 +27,7 @@ struct EvalParams {
   double *out;            // M results (S == 1) ...
   double *partial;        // ... or S x M partial sums
   const double *exptab;
+  ExpConsts ec;
   int64_t N, M, q0, chunk;
   int qstride, S, tile_nodes;
   double ich[KDEB200_MAX_DIM];  // -0.5 / variance_k
@@ -50,7 +51,7 @@ __device__ __forceinline__ void load_rec(const double *__restrict__ r, double (&
 
 // -0.5 * sum_k (x_k - mu_k)^2 / var_k   (distGauss! exponent, src/DualTree01.jl:32-44)
 template <int D, int S>
-__device__ __forceinline__ double quad(const double (&x)[D], const double (&r)[S], const double (&ich)[D]) {
+__device__ __forceinline__ double quad(const double (&x)[D], const double (&r)[S], const double *__restrict__ ich) {
   double acc = 0.0;
 #pragma unroll
   for (int k = 0; k < D; ++k) {
@@ -128,9 +129,7 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
     sum[i] = 0.0;
     self[i] = LOO ? (P.q0 + qi) : -1;
   }
-  double ich[D];
-#pragma unroll
-  for (int k = 0; k < D; ++k) ich[k] = P.ich[k];
+  const double *ich = P.ich;  // kernel-parameter space: used as c[0x0][..] operands, not registers
 
   // does the CTA's own index range overlap this split? (warp-uniform; only then test i == j)
   const int64_t qlo = P.q0 + qbase, qhi = qlo + EV_THREADS * Q;
@@ -152,8 +151,8 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
         load_rec<SE>(rec + (c + 1) * SE, rb);
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
-          e[0][i] = kde_exp_flush(quad<D>(x[i], ra, ich), tab);
-          e[1][i] = kde_exp_flush(quad<D>(x[i], rb, ich), tab);
+          e[0][i] = kde_exp_flush(quad<D>(x[i], ra, ich), tab, P.ec);
+          e[1][i] = kde_exp_flush(quad<D>(x[i], rb, ich), tab, P.ec);
         }
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
@@ -165,7 +164,7 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
         double ra[SE];
         load_rec<SE>(rec + c * SE, ra);
 #pragma unroll
-        for (int i = 0; i < Q; ++i) sum[i] = __fma_rn(kde_exp_flush(quad<D>(x[i], ra, ich), tab), ra[D], sum[i]);
+        for (int i = 0; i < Q; ++i) sum[i] = __fma_rn(kde_exp_flush(quad<D>(x[i], ra, ich), tab, P.ec), ra[D], sum[i]);
       }
     } else {
       for (int c = 0; c < cnt; ++c) {
@@ -173,7 +172,7 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
         load_rec<SE>(rec + c * SE, ra);
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
-          const double e = kde_exp_flush(quad<D>(x[i], ra, ich), tab);
+          const double e = kde_exp_flush(quad<D>(x[i], ra, ich), tab, P.ec);
           if (a + c != self[i]) sum[i] = __fma_rn(e, ra[D], sum[i]);  // leave-one-out (src/DualTree01.jl:146)
         }
       }
@@ -294,6 +293,7 @@ int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int6
   P.perm = (loo && scatter) ? bd->d_perm : nullptr;
   P.out = d_out;
   P.exptab = c.d_exptab;
+  P.ec = make_exp_consts();
   double norm = std::pow(2.0 * M_PI, (double)d / 2.0);  // src/DualTree01.jl:325-330
   for (int k = 0; k < d; ++k) {
     const double v = bw_var ? bw_var[k] : bd->hvar[k];

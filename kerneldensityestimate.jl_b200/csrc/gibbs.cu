@@ -167,6 +167,7 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
   P.draws = d_draws;
   P.tiles = d_tiles;
   P.exptab = c.d_exptab;
+  P.ec = make_exp_consts();
   P.randU = d_randU;
   P.randN = d_randN;
   P.points = d_points;

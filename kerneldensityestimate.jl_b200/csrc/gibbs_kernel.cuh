@@ -74,6 +74,7 @@ struct GibbsParams {
   const Draw *draws;
   const TileDesc *tiles;
   const double *exptab;
+  ExpConsts ec;
   const double *randU, *randN;  // injected streams or null (Philox)
   double *points;               // d x (s1-s0)
   int64_t *indices;             // M x (s1-s0)
@@ -93,7 +94,7 @@ struct GibbsParams {
 template <int D, bool MASK>
 struct Hoist {
   double mu[D];    // X or Malmost
-  double ich[D];   // variant A: -0.5 / (h_k + Calmost_k)
+  double ich[D];   // variant A: sqrt(0.5 / (h_k + Calmost_k))
   double cadd[D];  // variant C: Calmost_k
   bool act[D];     // dimension participates (partialDimMask logic, :270-285)
 };
@@ -122,8 +123,9 @@ __device__ __forceinline__ void pre_A(const double *__restrict__ r, const Hoist<
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     if (MASK && !h.act[k]) continue;
-    const double df = __dadd_rn(rr[k], -h.mu[k]);
-    acc = __fma_rn(__dmul_rn(df, df), h.ich[k], acc);
+    // e = (m - mu) * sqrt(0.5/c); acc -= e*e : the FMA reads e twice => two distinct register sources
+    const double e = __dmul_rn(__dadd_rn(rr[k], -h.mu[k]), h.ich[k]);
+    acc = __fma_rn(-e, e, acc);
   }
   arg = acc;
   sc = 1.0;
@@ -188,17 +190,17 @@ __device__ __forceinline__ void pre_node(const double *__restrict__ r, const Hoi
 }
 
 template <int VAR>
-__device__ __forceinline__ double fin_node(double arg, double sc, const double *__restrict__ tab) {
-  const double e = kde_exp_flush(arg, tab);
+__device__ __forceinline__ double fin_node(double arg, double sc, const double *__restrict__ tab, const ExpConsts &ec) {
+  const double e = kde_exp_flush(arg, tab, ec);
   return (VAR == VAR_C) ? __dmul_rn(e, sc) : e;
 }
 
 template <int D, bool MASK, int VAR>
 __device__ __forceinline__ double eval_node(const double *__restrict__ r, const Hoist<D, MASK> &h,
-                                            const double *__restrict__ tab) {
+                                            const double *__restrict__ tab, const ExpConsts &ec) {
   double arg, sc;
   pre_node<D, MASK, VAR>(r, h, arg, sc);
-  return fin_node<VAR>(arg, sc, tab);
+  return fin_node<VAR>(arg, sc, tab, ec);
 }
 
 // pass 1 over the tiles of one draw: sequential sum, checkpoints every G nodes
@@ -220,11 +222,11 @@ __device__ __forceinline__ void ring_issue(const Ring &R, int64_t q) {
 // consume one pipelined group: p = exp(arg)[*sc], sequential adds, checkpoint at chunk ends
 template <int VAR, int UNR>
 __device__ __forceinline__ void consume_group(const double (&arg)[UNR], const double (&sc)[UNR],
-                                              const double *__restrict__ tab, double &S, int &consumed, int &c,
-                                              double *__restrict__ ck, int G, int n) {
+                                              const double *__restrict__ tab, const ExpConsts &ec, double &S,
+                                              int &consumed, int &c, double *__restrict__ ck, int G, int n) {
   double p[UNR];
 #pragma unroll
-  for (int u = 0; u < UNR; ++u) p[u] = fin_node<VAR>(arg[u], sc[u], tab);
+  for (int u = 0; u < UNR; ++u) p[u] = fin_node<VAR>(arg[u], sc[u], tab, ec);
 #pragma unroll
   for (int u = 0; u < UNR; ++u) S = __dadd_rn(S, p[u]);
   consumed += UNR;
@@ -233,7 +235,7 @@ __device__ __forceinline__ void consume_group(const double (&arg)[UNR], const do
 
 template <int D, bool MASK, int VAR>
 __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h, const double *__restrict__ tab,
-                                        const Ring &R, int64_t &q, double *__restrict__ ck) {
+                                        const ExpConsts &ec, const Ring &R, int64_t &q, double *__restrict__ ck) {
   // UNR nodes per group.  Within a tile the groups are software-pipelined with two register sets
   // (A/B ping-pong, no rotation moves): stage 1 (record -> exponent) of group g is issued in the
   // same basic block as the exp chains of group g-1.  Fewer nodes per group at high d, where ptxas
@@ -258,19 +260,19 @@ __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h,
       for (; z + DG < full; z += DG) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u) pre_node<D, MASK, VAR>(rec + (size_t)(z + UNR + u) * stride, h, a1[u], s1[u]);
-        consume_group<VAR, UNR>(a0, s0, tab, S, consumed, c, ck, G, n);
+        consume_group<VAR, UNR>(a0, s0, tab, ec, S, consumed, c, ck, G, n);
 #pragma unroll
         for (int u = 0; u < UNR; ++u) pre_node<D, MASK, VAR>(rec + (size_t)(z + DG + u) * stride, h, a0[u], s0[u]);
-        consume_group<VAR, UNR>(a1, s1, tab, S, consumed, c, ck, G, n);
+        consume_group<VAR, UNR>(a1, s1, tab, ec, S, consumed, c, ck, G, n);
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) pre_node<D, MASK, VAR>(rec + (size_t)(z + UNR + u) * stride, h, a1[u], s1[u]);
-      consume_group<VAR, UNR>(a0, s0, tab, S, consumed, c, ck, G, n);
-      consume_group<VAR, UNR>(a1, s1, tab, S, consumed, c, ck, G, n);
+      consume_group<VAR, UNR>(a0, s0, tab, ec, S, consumed, c, ck, G, n);
+      consume_group<VAR, UNR>(a1, s1, tab, ec, S, consumed, c, ck, G, n);
       z = full;
     }
     for (; z < cnt; ++z) {  // small levels and the ragged end of the last tile: one node at a time
-      S = __dadd_rn(S, eval_node<D, MASK, VAR>(rec + (size_t)z * stride, h, tab));
+      S = __dadd_rn(S, eval_node<D, MASK, VAR>(rec + (size_t)z * stride, h, tab, ec));
       consumed += 1;
       if ((consumed & (G - 1)) == 0 || consumed == n) ck[c++] = S;
     }
@@ -282,8 +284,8 @@ __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h,
 
 // pass 2: locate the first z with target <= prefix(z) inside chunk cs (per-lane global loads)
 template <int D, bool MASK, int VAR>
-__device__ __forceinline__ int pass2(const Draw &dr, const Hoist<D, MASK> &h, const double *__restrict__ tab, int cs,
-                                  double S, double target) {
+__device__ __forceinline__ int pass2(const Draw &dr, const Hoist<D, MASK> &h, const double *__restrict__ tab,
+                                     const ExpConsts &ec, int cs, double S, double target) {
   constexpr int stride = (VAR == VAR_A) ? ((D + 2) & ~1) : ((2 * D + 2) & ~1);  // == dr.stride
   const int z0 = cs * dr.G;
   const int z1 = (z0 + dr.G < dr.n) ? z0 + dr.G : dr.n;
@@ -291,7 +293,7 @@ __device__ __forceinline__ int pass2(const Draw &dr, const Hoist<D, MASK> &h, co
   int zs = z1 - 1;
   bool found = false;
   for (int z = z0; z < z1; ++z) {
-    S = __dadd_rn(S, eval_node<D, MASK, VAR>(r, h, tab));
+    S = __dadd_rn(S, eval_node<D, MASK, VAR>(r, h, tab, ec));
     if (!found && target <= S) {
       zs = z;
       found = true;
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
 #pragma unroll
         for (int k = 0; k < D; ++k) {
           const double c = P.hvar[j][k] + h.cadd[k];
-          h.ich[k] = -0.5 / c;
+          h.ich[k] = sqrt(0.5 / c);
           if (!MASK || h.act[k]) prod *= c;
         }
         scale = kde_rsqrt(prod);
@@ -426,11 +428,11 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
 
       double pT;
       if (dr.variant == VAR_A)
-        pT = pass1<D, MASK, VAR_A>(dr, h, tab, R, q, ck);
+        pT = pass1<D, MASK, VAR_A>(dr, h, tab, P.ec, R, q, ck);
       else if (dr.variant == VAR_B)
-        pT = pass1<D, MASK, VAR_B>(dr, h, tab, R, q, ck);
+        pT = pass1<D, MASK, VAR_B>(dr, h, tab, P.ec, R, q, ck);
       else
-        pT = pass1<D, MASK, VAR_C>(dr, h, tab, R, q, ck);
+        pT = pass1<D, MASK, VAR_C>(dr, h, tab, P.ec, R, q, ck);
 
       // selectLabelOnLevel: the c-th call of this chain reads randU[(s*perU + c) - 1]
       int zs = 0;
@@ -466,11 +468,11 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
           } else {
             const double S0 = lo > 0 ? ck[lo - 1] : 0.0;
             if (dr.variant == VAR_A)
-              zs = pass2<D, MASK, VAR_A>(dr, h, tab, lo, S0, target);
+              zs = pass2<D, MASK, VAR_A>(dr, h, tab, P.ec, lo, S0, target);
             else if (dr.variant == VAR_B)
-              zs = pass2<D, MASK, VAR_B>(dr, h, tab, lo, S0, target);
+              zs = pass2<D, MASK, VAR_B>(dr, h, tab, P.ec, lo, S0, target);
             else
-              zs = pass2<D, MASK, VAR_C>(dr, h, tab, lo, S0, target);
+              zs = pass2<D, MASK, VAR_C>(dr, h, tab, P.ec, lo, S0, target);
           }
         }
       }
