@@ -135,7 +135,9 @@ __device__ __forceinline__ double kde_exp_core(double x, const double *__restric
   const double p = __fma_rn(__dmul_rn(q, r), r, r);
   const double T = tab[n & (KDE_EXP_TAB - 1)];
   const double y = __fma_rn(T, p, T);
-  return __hiloint2double(__double2hiint(y) + ((n & ~(KDE_EXP_TAB - 1)) << KDE_EXP_SHL), __double2loint(y));
+  // exponent: mask first, then one shift-add (LEA): hi(y) + ((n >> log2 TAB) << 20)
+  const int nm = n & ~(KDE_EXP_TAB - 1);
+  return __hiloint2double(__double2hiint(y) + (nm << KDE_EXP_SHL), __double2loint(y));
 }
 
 // Gibbs flavour: x < -700 (p < 1e-304) is clamped (or flushed to 0 with KDE_FLUSH_SELECT), negative NaN -> tiny
