@@ -49,6 +49,13 @@ static int init_device(int device) {
   c.device = device;
   c.sm_count = prop.multiProcessorCount;
   KDE_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  {  // keep freed blocks in the stream-ordered pool (the default returns them to the driver at every sync,
+     // which made tree create / destroy cost tens of milliseconds)
+    cudaMemPool_t pool;
+    KDE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    KDE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   KDE_CUDA(cudaEventCreate(&c.ev0));
   KDE_CUDA(cudaEventCreate(&c.ev1));
   double tab[KDE_EXP_TAB];

@@ -163,7 +163,7 @@ int eval_device_f32(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, 
   }
   if (!bd->d_leaf32) {  // one-time FP32 shadow of the leaf records (freed with the tree)
     double *d_cs = nullptr;
-    KDE_CUDA(cudaMalloc(&bd->d_leaf32, sizeof(float) * (size_t)bd->N * SF));
+    KDE_CUDA(cudaMallocAsync(&bd->d_leaf32, sizeof(float) * (size_t)bd->N * SF, st));
     KDE_CUDA(cudaMallocAsync(&d_cs, sizeof(cs), st));
     KDE_CUDA(cudaMemcpyAsync(d_cs, cs, sizeof(cs), cudaMemcpyHostToDevice, st));
     KDE_CUDA(cudaStreamSynchronize(st));

@@ -30,6 +30,7 @@ struct kdeb200_tree_s {
   int SA = 0, SC = 0, SE = 0;          // record strides in doubles (even => 16-byte aligned records)
   std::vector<kdeb200::Level> levels;  // levels[0] = {root}; levels[l], l = 1..depth
   int depth = 0;                       // last distinct level (all leaves)
+  char *d_base = nullptr;              // the single device allocation everything below points into
   double *d_buf = nullptr;             // all level records
   size_t buf_doubles = 0;
   int64_t *d_labels = nullptr;  // deepest level, level order: permutation + 1 (src/MSGibbs01.jl:615)
