@@ -459,8 +459,12 @@ def prodAppxMSGibbsS(npd0, trees, anFcns=None, anParams=None, Niter=3, addop=Non
         if Ndim(t) != d:
             raise KDEError("kdes must have same dimension")
     if Np is None:
+        if npd0 is None:
+            raise KDEError("prodAppxMSGibbsS: pass npd0 (its Npts is the number of samples) or Np")
         Np = Npts(npd0)
     Np = int(Np)
+    if Np < 0 or not (0 <= s0 <= (Np if s1 is None else s1) <= Np):
+        raise KDEError("prodAppxMSGibbsS: bad sample range")
     s1 = Np if s1 is None else int(s1)
     n = s1 - s0
     mask = None

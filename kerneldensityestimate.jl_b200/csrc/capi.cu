@@ -3,6 +3,7 @@
 // *_device variants are asynchronous on the caller's stream.
 #include <cmath>
 #include <limits>
+#include <mutex>
 #include <vector>
 
 #include "tree.cuh"
@@ -30,6 +31,11 @@ int philox_streams_device(uint64_t seed, int64_t Np, int64_t perU, int64_t perN,
                           cudaStream_t st);
 int pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms_out);
 int dfma_probe(int ilp, int blocks_per_sm, int threads, int iters, double *lane_ops_per_s);
+
+// The reference is single-threaded with module-level state; the library keeps one stream and one
+// event pair per process, so compute entry points are serialised (recursive: loo_entropy -> loo_partial).
+static std::recursive_mutex g_call_mu;
+#define KDE_SERIALISE() std::lock_guard<std::recursive_mutex> kde_lock__(::kdeb200::g_call_mu)
 
 // RAII device buffer on a stream
 struct DevBuf {
@@ -78,14 +84,19 @@ int kdeb200_tree_build_host(int d, int64_t N, const double *points, const double
 int kdeb200_tree_create(int d, int64_t N, const double *means, const double *bandwidth, const double *weights,
                         const int64_t *left_child, const int64_t *right_child, const int64_t *permutation,
                         kdeb200_tree_t *out) {
+  KDE_SERIALISE();
   if (!means || !bandwidth || !weights || !left_child || !right_child || !permutation)
     KDE_FAIL(2, "tree_create: NULL argument");
   return tree_create(d, N, means, bandwidth, weights, left_child, right_child, permutation, out);
 }
 
-int kdeb200_tree_destroy(kdeb200_tree_t t) { return tree_destroy(t); }
+int kdeb200_tree_destroy(kdeb200_tree_t t) {
+  KDE_SERIALISE();
+  return tree_destroy(t);
+}
 
 int kdeb200_tree_info(kdeb200_tree_t t, int *d, int64_t *N, int *nlevels, int64_t *device_bytes) {
+  KDE_SERIALISE();
   if (!t) KDE_FAIL(2, "tree_info: NULL tree");
   if (d) *d = t->d;
   if (N) *N = t->N;
@@ -104,6 +115,7 @@ int kdeb200_gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int
                          const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN, int64_t nN,
                          uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices,
                          int64_t *d_level_labels, void *stream) {
+  KDE_SERIALISE();
   if (int rc = ensure_init()) return rc;
   if (!trees || !d_points || !d_indices) KDE_FAIL(2, "gibbs_device: NULL argument");
   int launches = 0;
@@ -117,6 +129,7 @@ int kdeb200_gibbs(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter,
                   const uint8_t *dimmask, const double *randU, int64_t nU, const double *randN, int64_t nN,
                   uint64_t seed, int64_t s0, int64_t s1, double *points_out, int64_t *indices_out,
                   int64_t *level_labels_out) {
+  KDE_SERIALISE();
   if (int rc = ensure_init()) return rc;
   if (!trees || !points_out || !indices_out) KDE_FAIL(2, "gibbs: NULL argument");
   Context &c = ctx();
@@ -175,6 +188,7 @@ int kdeb200_gibbs(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter,
 
 int kdeb200_philox_streams(uint64_t seed, int64_t Np, int64_t perU, int64_t perN, double *randU_out,
                            double *randN_out) {
+  KDE_SERIALISE();
   if (int rc = ensure_init()) return rc;
   if (!randU_out || !randN_out || Np < 0 || perU < 1 || perN < 1) KDE_FAIL(2, "philox_streams: bad argument");
   Context &c = ctx();
@@ -190,6 +204,7 @@ int kdeb200_philox_streams(uint64_t seed, int64_t Np, int64_t perU, int64_t perN
 
 int kdeb200_eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int precision, double *d_out,
                         void *stream) {
+  KDE_SERIALISE();
   if (int rc = ensure_init()) return rc;
   if (!bd || !d_out) KDE_FAIL(2, "eval_device: NULL argument");
   if (!loo && !d_pos) KDE_FAIL(2, "eval_device: pos is NULL");
@@ -207,6 +222,7 @@ int kdeb200_eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int l
 }
 
 int kdeb200_eval(kdeb200_tree_t bd, const double *pos, int64_t M, int loo, int precision, double *p_out) {
+  KDE_SERIALISE();
   if (int rc = ensure_init()) return rc;
   if (!bd || !p_out) KDE_FAIL(2, "eval: NULL argument");
   if (!loo && !pos && M > 0) KDE_FAIL(2, "eval: pos is NULL");
@@ -235,6 +251,7 @@ int kdeb200_eval(kdeb200_tree_t bd, const double *pos, int64_t M, int loo, int p
 
 int kdeb200_loo_partial(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int64_t j1, double *sum_out,
                         int *zero_flag_out) {
+  KDE_SERIALISE();
   if (int rc = ensure_init()) return rc;
   if (!bd || !sum_out || !zero_flag_out) KDE_FAIL(2, "loo_partial: NULL argument");
   if (j0 < 0 || j1 > bd->N || j0 > j1) KDE_FAIL(3, "loo_partial: bad row range");
@@ -257,6 +274,7 @@ int kdeb200_loo_partial(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int
 }
 
 int kdeb200_loo_entropy(kdeb200_tree_t bd, const double *bw_var, double *H_out) {
+  KDE_SERIALISE();
   if (!bd || !H_out) KDE_FAIL(2, "loo_entropy: NULL argument");
   double s = 0.0;
   int flag = 0;
@@ -267,10 +285,12 @@ int kdeb200_loo_entropy(kdeb200_tree_t bd, const double *bw_var, double *H_out) 
 }
 
 int kdeb200_pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms) {
+  KDE_SERIALISE();
   return pipe_peak(which, iters, lane_ops_per_s, ms);
 }
 
 int kdeb200_dfma_probe(int ilp, int blocks_per_sm, int threads, int iters, double *lane_ops_per_s) {
+  KDE_SERIALISE();
   return dfma_probe(ilp, blocks_per_sm, threads, iters, lane_ops_per_s);
 }
 

@@ -2,9 +2,12 @@
 //
 // Same sum as eval.cu (evalDirect, src/DualTree01.jl:130-162) with the pair arithmetic in FP32:
 // coordinates are centred on the density's mean and pre-scaled by sqrt(0.5*log2(e)/variance_k) in
-// FP64 once per tree, so a pair costs d FADD + d FFMA + 1 MUFU.EX2 + 1 FFMA (MUFU-bound for
-// d <= 3: 16 ex2/clk/SM, the FMA pipe for d >= 4).  Per-tile FP32 partial sums are folded into an
-// FP64 accumulator, so the error does not grow with the number of components.
+// FP64 once per tree.  Components are stored in PAIRS, [x_0(a), x_0(b), .., x_{d-1}(a), x_{d-1}(b),
+// w(a), w(b)], so that one Blackwell packed-FP32 instruction (FADD2 / FFMA2, PTX add/fma.f32x2)
+// serves two components: per pair and query d FADD2 + d FFMA2 + 2 MUFU.EX2 + 1 FFMA2, i.e. 3.5 + 1
+// issue slots per evaluation at d = 3 against 8 MUFU cycles per warp -> MUFU-bound (16 ex2/clk/SM).
+// Per-tile FP32 partial sums are folded into an FP64 accumulator, so the error does not grow
+// with the number of components.
 #include <cmath>
 #include <vector>
 
@@ -18,34 +21,68 @@ constexpr int F32_STAGES = 3;
 constexpr int F32_TILE_BYTES = 8192;
 
 struct EvalF32Params {
-  const float *comps;      // N records [x'_0..x'_{d-1}, w], stride SF floats (16-byte multiple)
+  const float *comps;      // ceil(N/2) pair records, stride SP floats (16-byte multiple)
   const double *queries;   // raw FP64 coordinates, query i at queries + i*qstride
   const double *leafw;     // LOO: FP64 leaf records (for 1 - w_j), stride SE
   const int64_t *perm;
   double *out;
   int64_t N, M;
-  int qstride, SE, tile_nodes, loo;
+  int qstride, SE, tile_pairs, loo;
   double ctr[KDEB200_MAX_DIM], scl[KDEB200_MAX_DIM];
   double norm;
 };
 
 template <int D>
 struct F32Rec {
-  static constexpr int SF = (D + 1 + 3) & ~3;
+  static constexpr int SP = (2 * (D + 1) + 3) & ~3;  // floats per component pair
 };
 
-__global__ void prep_f32_kernel(const double *leaf, int SE, int D, int SF, int64_t N, const double *ctr_scl,
+typedef unsigned long long f32x2;  // two packed floats {lo, hi}
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float ex2_neg(float a) {  // 2^(-a): the negation is a free MUFU operand modifier
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a));
+  return e;
+}
+
+__global__ void prep_f32_kernel(const double *leaf, int SE, int D, int SP, int64_t N, const double *ctr_scl,
                                 float *out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  for (int k = 0; k < D; ++k) out[i * SF + k] = (float)((leaf[i * SE + k] - ctr_scl[k]) * ctr_scl[8 + k]);
-  out[i * SF + D] = (float)leaf[i * SE + D];
-  for (int k = D + 1; k < SF; ++k) out[i * SF + k] = 0.f;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+  if (2 * p >= N) return;
+  for (int h = 0; h < 2; ++h) {
+    const int64_t i = 2 * p + h;
+    const bool ok = i < N;  // an odd N is padded with a zero-weight component
+    for (int k = 0; k < D; ++k) out[p * SP + 2 * k + h] = ok ? (float)((leaf[i * SE + k] - ctr_scl[k]) * ctr_scl[8 + k]) : 0.f;
+    out[p * SP + 2 * D + h] = ok ? (float)leaf[i * SE + D] : 0.f;
+  }
+  for (int k = 2 * (D + 1); k < SP; ++k) out[p * SP + k] = 0.f;
 }
 
 template <int D, bool LOO>
 __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_constant__ EvalF32Params P) {
-  constexpr int SF = F32Rec<D>::SF;
+  constexpr int SP = F32Rec<D>::SP;
   constexpr int Q = F32_Q;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *tiles = reinterpret_cast<float *>(smem_raw);
@@ -56,21 +93,22 @@ __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_cons
     mbar_fence_init();
   }
   __syncthreads();
-  const int TN = P.tile_nodes;
-  const int ntiles = (int)((P.N + TN - 1) / TN);
+  const int TP = P.tile_pairs;
+  const int64_t npairs = (P.N + 1) / 2;
+  const int ntiles = (int)((npairs + TP - 1) / TP);
   auto issue = [&](int t) {
-    const int64_t a = (int64_t)t * TN;
-    const int64_t cnt = (P.N - a < TN) ? (P.N - a) : TN;
-    const uint32_t bytes = (uint32_t)(cnt * SF * sizeof(float));
+    const int64_t a = (int64_t)t * TP;
+    const int64_t cnt = (npairs - a < TP) ? (npairs - a) : TP;
+    const uint32_t bytes = (uint32_t)(cnt * SP * sizeof(float));
     uint64_t *bar = &bars[t % F32_STAGES];
     mbar_expect_tx(bar, bytes);
-    tma_bulk_g2s(tiles + (size_t)(t % F32_STAGES) * (F32_TILE_BYTES / 4), P.comps + a * SF, bytes, bar);
+    tma_bulk_g2s(tiles + (size_t)(t % F32_STAGES) * (F32_TILE_BYTES / 4), P.comps + a * SP, bytes, bar);
   };
   if (tid == 0)
     for (int t = 0; t < F32_STAGES && t < ntiles; ++t) issue(t);
 
   const int64_t qbase = (int64_t)blockIdx.x * (F32_THREADS * Q);
-  float x[Q][D];
+  f32x2 x2[Q][D];  // each query coordinate broadcast into both halves
   double sum[Q];
   int64_t self[Q];
 #pragma unroll
@@ -79,45 +117,79 @@ __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_cons
     if (qi >= P.M) qi = P.M - 1;
     const double *src = P.queries + qi * (int64_t)P.qstride;
 #pragma unroll
-    for (int k = 0; k < D; ++k) x[i][k] = (float)((src[k] - P.ctr[k]) * P.scl[k]);
+    for (int k = 0; k < D; ++k) {
+      const float v = (float)((src[k] - P.ctr[k]) * P.scl[k]);
+      x2[i][k] = pack2(v, v);
+    }
     sum[i] = 0.0;
     self[i] = LOO ? qi : -1;
   }
   const int64_t qlo = qbase, qhi = qbase + F32_THREADS * Q;
 
   for (int t = 0; t < ntiles; ++t) {
-    const int64_t a = (int64_t)t * TN;
-    const int cnt = (int)((P.N - a < TN) ? (P.N - a) : TN);
+    const int64_t a = (int64_t)t * TP;  // first pair of the tile
+    const int cnt = (int)((npairs - a < TP) ? (npairs - a) : TP);
     mbar_wait(&bars[t % F32_STAGES], (uint32_t)((t / F32_STAGES) & 1));
     const float *rec = tiles + (size_t)(t % F32_STAGES) * (F32_TILE_BYTES / 4);
-    const bool check = LOO && (a < qhi) && (a + cnt > qlo);
-    float part[Q];
+    const bool check = LOO && (2 * a < qhi) && (2 * (a + cnt) > qlo);
+    f32x2 part[Q];
 #pragma unroll
-    for (int i = 0; i < Q; ++i) part[i] = 0.f;
-#pragma unroll 4
-    for (int c = 0; c < cnt; ++c) {
-      float r[SF];
+    for (int i = 0; i < Q; ++i) part[i] = 0ull;
+    if (!check) {
+#pragma unroll 2
+      for (int c = 0; c < cnt; ++c) {
+        f32x2 r2[SP / 2];
 #pragma unroll
-      for (int k = 0; k < SF; k += 4) {
-        const float4 v = *reinterpret_cast<const float4 *>(rec + c * SF + k);
-        r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
-      }
-#pragma unroll
-      for (int i = 0; i < Q; ++i) {
-        float nacc = 0.f;
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-          const float df = x[i][k] - r[k];
-          nacc = __fmaf_rn(-df, df, nacc);
+        for (int k = 0; k < SP / 2; k += 2) {
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(rec + c * SP + 2 * k);
+          r2[k] = v.x;
+          r2[k + 1] = v.y;
         }
-        float e;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(nacc));
-        const float w = (check && a + c == self[i]) ? 0.f : r[D];  // leave-one-out
-        part[i] = __fmaf_rn(e, w, part[i]);
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+          f32x2 df = sub2(x2[i][0], r2[0]);
+          f32x2 acc = mul2(df, df);
+#pragma unroll
+          for (int k = 1; k < D; ++k) {
+            df = sub2(x2[i][k], r2[k]);
+            acc = fma2(df, df, acc);
+          }
+          float alo, ahi;
+          unpack2(acc, alo, ahi);
+          part[i] = fma2(pack2(ex2_neg(alo), ex2_neg(ahi)), r2[D], part[i]);
+        }
+      }
+    } else {  // tiles that overlap the CTA's own rows: leave-one-out test per component
+      for (int c = 0; c < cnt; ++c) {
+        const float *r = rec + c * SP;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+          float xs[D], dummy;
+#pragma unroll
+          for (int k = 0; k < D; ++k) unpack2(x2[i][k], xs[k], dummy);
+          float plo, phi;
+          unpack2(part[i], plo, phi);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              const float df = xs[k] - r[2 * k + h];
+              acc = __fmaf_rn(df, df, acc);
+            }
+            const float w = (2 * (a + c) + h == self[i]) ? 0.f : r[2 * D + h];
+            plo = __fmaf_rn(ex2_neg(acc), w, plo);
+          }
+          part[i] = pack2(plo, phi);
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < Q; ++i) sum[i] += (double)part[i];
+    for (int i = 0; i < Q; ++i) {
+      float plo, phi;
+      unpack2(part[i], plo, phi);
+      sum[i] += (double)plo + (double)phi;
+    }
     __syncthreads();
     if (tid == 0 && t + F32_STAGES < ntiles) issue(t + F32_STAGES);
   }
@@ -150,7 +222,8 @@ int eval_device_f32(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, 
                     int *launches) {
   if (M <= 0) return 0;
   const int d = bd->d;
-  const int SF = (d + 1 + 3) & ~3;
+  const int SP = (2 * (d + 1) + 3) & ~3;
+  const int64_t npairs = (bd->N + 1) / 2;
   EvalF32Params P;
   double norm = std::pow(2.0 * M_PI, (double)d / 2.0);
   double cs[16];
@@ -163,12 +236,12 @@ int eval_device_f32(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, 
   }
   if (!bd->d_leaf32) {  // one-time FP32 shadow of the leaf records (freed with the tree)
     double *d_cs = nullptr;
-    KDE_CUDA(cudaMallocAsync(&bd->d_leaf32, sizeof(float) * (size_t)bd->N * SF, st));
+    KDE_CUDA(cudaMallocAsync(&bd->d_leaf32, sizeof(float) * (size_t)npairs * SP, st));
     KDE_CUDA(cudaMallocAsync(&d_cs, sizeof(cs), st));
     KDE_CUDA(cudaMemcpyAsync(d_cs, cs, sizeof(cs), cudaMemcpyHostToDevice, st));
     KDE_CUDA(cudaStreamSynchronize(st));
-    prep_f32_kernel<<<(unsigned)((bd->N + 255) / 256), 256, 0, st>>>(bd->d_leaf, bd->SE, d, SF, bd->N, d_cs,
-                                                                     bd->d_leaf32);
+    prep_f32_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(bd->d_leaf, bd->SE, d, SP, bd->N, d_cs,
+                                                                      bd->d_leaf32);
     KDE_CUDA(cudaGetLastError());
     KDE_CUDA(cudaFreeAsync(d_cs, st));
     if (launches) *launches += 1;
@@ -184,9 +257,9 @@ int eval_device_f32(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, 
   P.M = M;
   P.loo = loo;
   P.norm = norm;
-  int TN = 1;
-  while (TN * 2 * SF * 4 <= F32_TILE_BYTES) TN *= 2;
-  P.tile_nodes = TN;
+  int TP = 1;
+  while (TP * 2 * SP * 4 <= F32_TILE_BYTES) TP *= 2;
+  P.tile_pairs = TP;
   const size_t smem = F32_STAGES * F32_TILE_BYTES;
   const unsigned grid = (unsigned)((M + F32_THREADS * F32_Q - 1) / (F32_THREADS * F32_Q));
   cudaError_t e = cudaErrorInvalidValue;
