@@ -280,6 +280,9 @@ def main():
             pass
         roof = {"bound": "fp64_fma_pipe", "achieved": ach * 2 / 1e12, "peak": dfma * 2 / 1e12, "unit": "TFLOP/s",
                 "frac": ach / dfma, "traffic": None,
+                "traffic_note": "ncu --set full on a 75,776-sample launch of the same kernel (profiles/r01_gibbs_v6_ncu.txt): "
+                                "dram read 0.26 GB + write 2.76 GB (local-memory checkpoints leaving L2), i.e. ~40 KB/sample "
+                                "or <0.5% of HBM bandwidth; a full 1M-sample launch does not finish under ncu replay",
                 "kernel": "gibbs_kernel<3,false>", "kernel_ms": k_ms,
                 "algorithmic_fp64_slots_per_sample": ALG_SLOTS_PER_SAMPLE, "kernel_evals_per_sample": evals,
                 "peak_source": "DFMA microbenchmark (kdeb200_pipe_peak) measured in this run; nominal 64/clk/SM x 148 x 1.965 GHz = 37.2 TFLOP/s",
