@@ -40,6 +40,7 @@ def compare(ktrees, otrees, Np, T, rng, add_entropy=True, mask=None):
     (3, 6, 100, 100, 5),      # testProds default
     (2, 4, 100, 100, 5), (4, 6, 100, 200, 10), (3, 5, 300, 100, 5), (2, 7, 100, 300, 5), (3, 2, 100, 100, 100),
     (1, 2, 64, 150, 3), (3, 3, 33, 130, 5), (5, 3, 50, 64, 2), (8, 2, 40, 64, 2), (1, 3, 2, 50, 5),
+    (6, 2, 700, 40, 2), (7, 3, 300, 40, 1), (4, 2, 2000, 64, 2), (2, 2, 5000, 40, 1),
     (2, 3, 1, 40, 3), (3, 1, 50, 40, 3), (2, 16, 20, 33, 1), (3, 2, 100, 1, 5), (2, 2, 100, 100, 0),
 ])
 def test_injected_streams_match_oracle(d, M, N, Np, T):
