@@ -306,7 +306,10 @@ def main():
             t0 = time.perf_counter()
             O.gibbs(otrees, n, NITER, U, G, nthreads=cores)
             dt = time.perf_counter() - t0
-            cpu = {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            t0 = time.perf_counter()
+            O.gibbs(otrees, 16, NITER, U, G, nthreads=1)
+            one = 16 / (time.perf_counter() - t0)
+            cpu = {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": "port", "one_thread_value": one,
                    "sample": "%d of %d samples of the same workload in %.1f s (literal C restatement of the reference, OpenMP over chains; the reference itself is single-threaded Julia, not installed)" % (n, n_per, dt)}
         out = {
             "metric": "product samples/sec (Gibbs, Niter=5)", "value": value, "unit": "samples/s", "n_gpus": world,

@@ -33,6 +33,17 @@ if "c5" in which:
         else:
             out["c5_f32"]["max_rel_err_vs_f64"] = float(np.max(np.abs(v - ref) / ref))
     out["c5_tree_build_host_s"] = t_build
+    if "--no-cpu" not in sys.argv:  # CPU port on a bounded sample of the queries
+        from oracle import oracle as O
+        import bench as _b
+        cores = _b.host_cores()
+        o = O.OKDE.kde_bw(pts, silverman(pts))
+        mq = 256
+        t0 = time.perf_counter(); o.evaluate(pos[:, :mq]); t1 = time.perf_counter() - t0
+        mq2 = 256 * cores
+        t0 = time.perf_counter(); o.evaluate(pos[:, :mq2], nthreads=cores); tn = time.perf_counter() - t0
+        out["c5_cpu_port"] = {"one_thread_evals_per_s": float(N) * mq / t1, "all_cores_evals_per_s": float(N) * mq2 / tn, "cores": cores,
+                              "sample": "%d and %d of %d queries against all %d components" % (mq, mq2, M, N)}
 if "c3" in which:
     N = 20_000 if small else 100_000
     rng = np.random.default_rng(3)
@@ -44,6 +55,16 @@ if "c3" in which:
     evals = float(N) * N
     out["c3_one_nLOO_LL"] = {"N": N, "kernel_ms": ms, "wall_ms": one * 1e3, "evals_per_s": evals / (ms * 1e-3),
                              "roofline_frac": evals * 17 / (ms * 1e-3) / dfma, "algorithmic_slots_per_eval": 17, "H": H, "launches": nl}
+    if "--no-cpu" not in sys.argv:
+        from oracle import oracle as O
+        import bench as _b
+        cores = _b.host_cores()
+        o1 = O.OKDE.kde_bw(K.getPoints(p1), K.getBW(p1)[:, 0], K.getWeights(p1))
+        mq = 64 * cores
+        t0 = time.perf_counter(); o1.evaluate(K.getPoints(p1)[:, :mq], nthreads=cores); tn = time.perf_counter() - t0
+        out["c3_cpu_port"] = {"all_cores_evals_per_s": float(N) * mq / tn, "cores": cores,
+                              "sample": "%d of %d rows of one nLOO_LL (same arithmetic, no self-skip)" % (mq, N),
+                              "extrapolated_one_nLOO_LL_s": tn * N / mq}
     t0 = time.perf_counter(); p = K.kde(pts); total = time.perf_counter() - t0
     out["c3_full_kde_lcv"] = {"N": N, "dims": 4, "wall_s": total, "bandwidth": K.getBW(p)[:, 0].tolist()}
 print(json.dumps(out, indent=1))
