@@ -102,16 +102,15 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t sample, 
 #else
 #error "KDE_EXP_TAB must be 256 or 2048"
 #endif
-// The four constants travel in the kernel-parameter struct (ExpConsts) so that ptxas uses them as
-// c[0x0][..] operands: a DFMA with three distinct REGISTER sources issues at 2/3 rate on this part
-// (register-bank limit, tools/micro/ops.cu), one with a constant-bank or immediate operand at full rate.
+// The constants travel in the kernel-parameter struct (ExpConsts) so that ptxas can use them as
+// c[0x0][..] / uniform-register operands: a DFMA with three distinct REGISTER sources issues at 2/3 rate on
+// this part (register-bank limit, tools/micro/ops.cu), one with a constant or immediate operand at full rate.
 struct ExpConsts {
   double k;      // TAB/ln2
-  double shift;  // 1.5 * 2^52: the low word of x*TAB/ln2 + shift is n = rint(x*TAB/ln2)
   double c1;     // -ln2/TAB (rounded)
   double sixth;  // 1/6
 };
-inline ExpConsts make_exp_consts() { return ExpConsts{KDE_EXP_K, 6755399441055744.0, KDE_EXP_C1, 1.6666666666666666e-01}; }
+inline ExpConsts make_exp_consts() { return ExpConsts{KDE_EXP_K, KDE_EXP_C1, 1.6666666666666666e-01}; }
 
 // exp(x) = 2^(n / TAB) * e^r = 2^(n >> log2 TAB) * T[n mod TAB] * e^r,  n = rint(x*TAB/ln2), |r| <= ln2/(2 TAB).
 //   TAB = 2048 (16 KB shared memory): degree-3 Taylor (truncation r^4/24 <= 3.4e-17)  -> 7 FP64 instructions
@@ -140,31 +139,15 @@ __device__ __forceinline__ double kde_exp_core(double x, const double *__restric
   return __hiloint2double(__double2hiint(y) + (nm << KDE_EXP_SHL), __double2loint(y));
 }
 
-// Gibbs flavour: x < -700 (p < 1e-304) is clamped (or flushed to 0 with KDE_FLUSH_SELECT), negative NaN -> tiny
-// (the reference maps NaN weights to 0, src/MSGibbs01.jl:302).  A flushed term can never matter:
-// either pT >= 1e-99 and the term is < 1e-205 of it, or every term is that small and the
-// pT < 1e-99 fallback (:311) fires with or without it.  Integer compares: no FP64-pipe cost.
+// Clamped flavour: x < -700 is replaced by -700 with ONE integer instruction on the high word (negative NaN
+// becomes tiny too; the reference maps NaN weights to 0, src/MSGibbs01.jl:302).  A term below e^-700 ~ 1e-304
+// can never matter in the Gibbs kernel: either pT >= 1e-99 and the term is < 1e-205 of it, or every term is
+// that small and the pT < 1e-99 fallback (:311) fires with or without it.  The evaluation kernel uses the
+// same clamp and recomputes exactly any row whose total is tiny.  x <= 700 is the caller's contract
+// (exponents are ln w plus non-positive terms, plus at most -0.5 sum ln b_k).
 __device__ __forceinline__ double kde_exp_flush(double x, const double *__restrict__ tab, const ExpConsts &ec) {
-#ifdef KDE_FLUSH_SELECT
-  const double y = kde_exp_core(x, tab, ec);
-  const int hx = __double2hiint(x);
-  const bool under = (unsigned)hx > 0xC085E000u;
-  const bool over = hx > 0x4085E000;
-  const int hi = under ? 0 : (over ? 0x7FF00000 : __double2hiint(y));
-  const int lo = (under || over) ? 0 : __double2loint(y);
-  return __hiloint2double(hi, lo);
-#else
-  // one integer op: clamp the high word so that x >= -700 (terms below e^-700 ~ 1e-304 are
-  // replaced by ~1e-304, which is equally irrelevant -- see above); x <= 700 is the caller's
-  // contract (exponents are ln w plus non-positive terms, plus at most -0.5 sum ln b_k).
   const unsigned hx = min((unsigned)__double2hiint(x), 0xC085E000u);
   return kde_exp_core(__hiloint2double((int)hx, __double2loint(x)), tab, ec);
-#endif
-}
-
-// x < -700 (or negative NaN) for arguments that are never positive: one unsigned compare
-__device__ __forceinline__ bool kde_exp_below_range(double x) {
-  return (unsigned)__double2hiint(x) > 0xC085E000u;
 }
 
 // reciprocal / reciprocal square root of a normal, positive double without the libdevice

@@ -8,7 +8,7 @@
 // Mapping: one thread owns Q query points (registers), the CTA streams the component records
 // [x_0..x_{d-1}, w] (leaf order, the reference's summation order) through a 3-stage shared-memory
 // ring filled by 1-D TMA bulk copies; every lane reads the same record (broadcast LDS), so the
-// kernel is bound by the FP64 pipe (3d + 11 DFMA-class instructions per pair), not by memory.
+// kernel is bound by the FP64 pipe (3d + 8 FP64 instructions per pair), not by memory.
 #include <cmath>
 #include <vector>
 

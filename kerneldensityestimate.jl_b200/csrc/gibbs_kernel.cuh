@@ -14,15 +14,16 @@
 // up to exp rounding) and checkpoints the running sum every G nodes (<= 64 checkpoints, local
 // memory); pass 2 re-evaluates only the chunk that contains u * pT, from global memory.
 // The arithmetic of one kernel evaluation is restructured:
-//   leaf levels (uniform bandwidth): 1/c_k and the normaliser hoisted out of the node loop,
-//     ln w folded into the exponent                       -> 3d + 11 FP64-pipe instr / node
+//   leaf levels (uniform bandwidth): sqrt(0.5/c_k) and the normaliser hoisted out of the node loop,
+//     ln w folded into the exponent                       -> 3d + 8 FP64-pipe instr / node
 //   internal levels, sampleIndices!: -0.5/b_k and ln w - 0.5 sum ln b_k precomputed per node
-//   internal levels, sampleIndex   : c_k = b_k + Calmost_k, sum_k ln c_k -> one rsqrt(prod c_k)
+//   internal levels, sampleIndex   : c_k = b_k + Calmost_k, sum_k ln c_k -> one rsqrt(prod c_k), which also
+//     yields the d reciprocals at d = 3                   -> 34 FP64-pipe instr / node
+#pragma once
 #include <cmath>
 #include <cstring>
 #include <vector>
 
-#pragma once
 #include "tree.cuh"
 
 namespace kdeb200 {

@@ -9,7 +9,7 @@ namespace kdeb200 { void set_error(const char*, ...) {} }
 
 // VAR: 0 = A (hoisted), 1 = C (per-dim rcp + rsqrt), 2 = C' (one rsqrt of the product, reciprocals by products)
 template <int VAR, int UNR, bool MUFU>
-__global__ void __launch_bounds__(128, 4) k(int iters, const double *in, double *out) {
+__global__ void __launch_bounds__(128, 4) k(int iters, const double *in, double *out, const __grid_constant__ ExpConsts ec) {
   __shared__ double tab[KDE_EXP_TAB];
   for (int i = threadIdx.x; i < KDE_EXP_TAB; i += blockDim.x) tab[i] = in[i & 63];
   __syncthreads();
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(128, 4) k(int iters, const double *in, double 
         arg = __fma_rn(quad, -0.5, lw[u]);
         if (MUFU) sc = kde_rsqrt(prod); else { double e = __fma_rn(-prod, 0.25, 1.0); double uu = __dmul_rn(__fma_rn(e, 0.375, 0.5), e); sc = __fma_rn(0.5, uu, 0.5); }
       }
-      double e = kde_exp_flush(arg, tab);
+      double e = kde_exp_flush(arg, tab, ec);
       p[u] = VAR ? __dmul_rn(e, sc) : e;
     }
 #pragma unroll
@@ -75,9 +75,9 @@ template <int VAR, int UNR, bool MUFU>
 void run(const char *name, int fp64_per_eval, int bps, const double *din, double *dout) {
   int iters = 20000;
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-  k<VAR, UNR, MUFU><<<148 * bps, 128>>>(iters / 10, din, dout);
+  k<VAR, UNR, MUFU><<<148 * bps, 128>>>(iters / 10, din, dout, make_exp_consts());
   cudaEventRecord(a);
-  k<VAR, UNR, MUFU><<<148 * bps, 128>>>(iters, din, dout);
+  k<VAR, UNR, MUFU><<<148 * bps, 128>>>(iters, din, dout, make_exp_consts());
   cudaEventRecord(b); cudaEventSynchronize(b);
   float ms; cudaEventElapsedTime(&ms, a, b);
   double evals = 148.0 * bps * 128 * (double)iters * UNR;
@@ -89,9 +89,9 @@ int main() {
   double h[256]; for (int i = 0; i < 256; ++i) h[i] = 0.5 + 0.01 * i; for (int j = 0; j < 64; ++j) h[j] = exp2(j / 64.0);
   double *din, *dout; cudaMalloc(&din, sizeof(h)); cudaMalloc(&dout, 8 * 148 * 8 * 128); cudaMemcpy(din, h, sizeof(h), cudaMemcpyHostToDevice);
   for (int bps = 2; bps <= 4; bps *= 2) {
-    run<0, 1, true>("A unr1", 20, bps, din, dout);
-    run<0, 2, true>("A unr2", 20, bps, din, dout);
-    run<0, 4, true>("A unr4", 20, bps, din, dout);
+    run<0, 1, true>("A unr1", 17, bps, din, dout);
+    run<0, 2, true>("A unr2", 17, bps, din, dout);
+    run<0, 4, true>("A unr4", 17, bps, din, dout);
     run<1, 1, true>("C unr1 (MUFU)", 41, bps, din, dout);
     run<1, 2, true>("C unr2 (MUFU)", 41, bps, din, dout);
     run<1, 4, true>("C unr4 (MUFU)", 41, bps, din, dout);
