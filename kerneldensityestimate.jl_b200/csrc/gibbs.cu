@@ -74,6 +74,8 @@ static void build_schedule(const kdeb200_tree_t *trees, int M, int L, int T, boo
         }
         int G = 1;
         while ((int64_t)G * GB_MAXCK < lv.n) G *= 2;
+        const int dg = gb_dg(t->d, dr.variant);
+        if (G < dg && lv.n >= 2 * dg) G = dg;  // pass 1 checkpoints per whole double group
         dr.G = G;
         dr.nchunks = (int)((lv.n + G - 1) / G);
         int tn = 1;

@@ -44,6 +44,11 @@ constexpr int GB_MAXCK = 64;  // checkpoints per draw
 
 enum : int { VAR_A = 0, VAR_B = 1, VAR_C = 2 };
 
+// nodes per software-pipelined group / double group of pass 1 (host and device must agree: the host
+// never picks a checkpoint chunk smaller than one double group once a level has two of them)
+__host__ __device__ constexpr int gb_unr(int D, int var) { return (D <= 4) ? ((var == VAR_C) ? GB_UNROLL_C : GB_UNROLL_A) : (D <= 5 ? 2 : 1); }
+__host__ __device__ constexpr int gb_dg(int D, int var) { return 2 * gb_unr(D, var); }
+
 struct alignas(16) Draw {
   const double *rec;        // evaluation records of this level (variant-specific layout)
   const double *rec_state;  // records the chain state is refreshed from ([m.., lnw] or [m.., b.., lnw])
@@ -220,18 +225,15 @@ __device__ __forceinline__ void ring_issue(const Ring &R, int64_t q) {
   tma_bulk_g2s(R.tiles + (size_t)(q % GB_STAGES) * (GB_TILE_BYTES / 8), td.src, td.bytes, bar);
 }
 
-// consume one pipelined group: p = exp(arg)[*sc], sequential adds, checkpoint at chunk ends
+// consume one pipelined group: p = exp(arg)[*sc], sequential adds
 template <int VAR, int UNR>
 __device__ __forceinline__ void consume_group(const double (&arg)[UNR], const double (&sc)[UNR],
-                                              const double *__restrict__ tab, const ExpConsts &ec, double &S,
-                                              int &consumed, int &c, double *__restrict__ ck, int G, int n) {
+                                              const double *__restrict__ tab, const ExpConsts &ec, double &S) {
   double p[UNR];
 #pragma unroll
   for (int u = 0; u < UNR; ++u) p[u] = fin_node<VAR>(arg[u], sc[u], tab, ec);
 #pragma unroll
   for (int u = 0; u < UNR; ++u) S = __dadd_rn(S, p[u]);
-  consumed += UNR;
-  if ((consumed & (G - 1)) == 0 || consumed == n) ck[c++] = S;
 }
 
 template <int D, bool MASK, int VAR>
@@ -241,7 +243,7 @@ __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h,
   // (A/B ping-pong, no rotation moves): stage 1 (record -> exponent) of group g is issued in the
   // same basic block as the exp chains of group g-1.  Fewer nodes per group at high d, where ptxas
   // 12.9 segfaults on wide unrolls.
-  constexpr int UNR = (D <= 4) ? ((VAR == VAR_C) ? GB_UNROLL_C : GB_UNROLL_A) : (D <= 5 ? 2 : 1);
+  constexpr int UNR = gb_unr(D, VAR);
   constexpr int DG = 2 * UNR;
   constexpr int stride = (VAR == VAR_A) ? ((D + 2) & ~1) : ((2 * D + 2) & ~1);  // == dr.stride
   const int n = dr.n, G = dr.G;
@@ -253,7 +255,8 @@ __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h,
     mbar_wait(&R.bars[q % GB_STAGES], (uint32_t)((q / GB_STAGES) & 1));
     const double *rec = R.tiles + (size_t)(q % GB_STAGES) * (GB_TILE_BYTES / 8);
     int z = 0;
-    if (D <= 6 && G >= UNR && cnt >= DG) {  // checkpoints fall on group boundaries (d >= 7: ptxas 12.9 segfaults on the pipelined body)
+    if (D <= 6 && G >= DG && cnt >= DG) {  // checkpoints fall on double-group boundaries (the host never picks a
+                                           // smaller chunk for n >= 2 DG); d >= 7: ptxas 12.9 segfaults on this body
       const int full = cnt & ~(DG - 1);
       double a0[UNR], s0[UNR], a1[UNR], s1[UNR];
 #pragma unroll
@@ -261,15 +264,19 @@ __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h,
       for (; z + DG < full; z += DG) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u) pre_node<D, MASK, VAR>(rec + (size_t)(z + UNR + u) * stride, h, a1[u], s1[u]);
-        consume_group<VAR, UNR>(a0, s0, tab, ec, S, consumed, c, ck, G, n);
+        consume_group<VAR, UNR>(a0, s0, tab, ec, S);
 #pragma unroll
         for (int u = 0; u < UNR; ++u) pre_node<D, MASK, VAR>(rec + (size_t)(z + DG + u) * stride, h, a0[u], s0[u]);
-        consume_group<VAR, UNR>(a1, s1, tab, ec, S, consumed, c, ck, G, n);
+        consume_group<VAR, UNR>(a1, s1, tab, ec, S);
+        consumed += DG;
+        if ((consumed & (G - 1)) == 0) ck[c++] = S;
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) pre_node<D, MASK, VAR>(rec + (size_t)(z + UNR + u) * stride, h, a1[u], s1[u]);
-      consume_group<VAR, UNR>(a0, s0, tab, ec, S, consumed, c, ck, G, n);
-      consume_group<VAR, UNR>(a1, s1, tab, ec, S, consumed, c, ck, G, n);
+      consume_group<VAR, UNR>(a0, s0, tab, ec, S);
+      consume_group<VAR, UNR>(a1, s1, tab, ec, S);
+      consumed += DG;
+      if ((consumed & (G - 1)) == 0 || consumed == n) ck[c++] = S;
       z = full;
     }
     for (; z < cnt; ++z) {  // small levels and the ragged end of the last tile: one node at a time
