@@ -79,3 +79,13 @@ def test_host_api_mirrors(built):
         K.kde(pts, [0.1, 0.2])
     with pytest.raises(K.KDEError):
         K.kde(pts, [0.1], addop=(lambda a, b: a + b,))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/kdeb200.h must be consumable by a C compiler (the Julia ccall / cgo / JNI side sees C)."""
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text('#include "kdeb200.h"\nint main(void) { kdeb200_tree_t t = 0; int n = 0; (void)t;\n'
+                   '  return kdeb200_device_count(&n) == 0 ? kdeb200_version() - kdeb200_version() : 0; }\n')
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "use.o")])
