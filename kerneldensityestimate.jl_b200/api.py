@@ -29,7 +29,8 @@ __all__ = [
     "KDEError", "BallTree", "BallTreeDensity", "kde", "kde_bang", "getPoints", "getBW", "getWeights", "marginal",
     "sample", "rand", "resample", "evaluateDualTree", "evalAvgLogL", "entropy", "kld", "minkld", "nLOO_LL", "golden",
     "ksize", "neighborMinMax", "updateBandwidth", "prodAppxMSGibbsS", "Ndim", "Npts", "init", "gibbs_sizes",
-    "philox_streams", "pipe_peak", "last_kernel_ms", "F64", "F32",
+    "philox_streams", "pipe_peak", "last_kernel_ms", "F64", "F32", "prod", "getKDERange", "getKDERangeLinspace",
+    "getKDEMax", "getKDEMean", "getKDEfit", "intersIntgAppxIS", "to_string", "from_string",
 ]
 
 F64, F32 = 0, 1
@@ -343,6 +344,100 @@ def minkld(p, q):
     return min(abs(kld(p, q)), abs(kld(q, p)))
 
 
+# ----------------------------------------------- thin host wrappers over the evaluation seam ----
+# (src/DualTree01.jl:512-618: out of scope as kernels -- they only call evaluateDualTree / marginal
+#  and speed up for free once the seam is on the GPU; mirrored so a user of the reference finds them)
+def getKDERange(bd, extend=0.1):
+    """src/DualTree01.jl:512-550; bd may be one density or a list (union of the ranges)."""
+    if isinstance(bd, (list, tuple)):
+        r = getKDERange(bd[0], extend)
+        for b in bd[1:]:
+            t = getKDERange(b, extend)
+            r[:, 0] = np.minimum(r[:, 0], t[:, 0])
+            r[:, 1] = np.maximum(r[:, 1], t[:, 1])
+        return r
+    pts = getPoints(bd)
+    lo, hi = pts.min(axis=1), pts.max(axis=1)
+    dr = extend * (hi - lo)
+    return np.stack([lo - dr, hi + dr], axis=1)
+
+
+def getKDERangeLinspace(bd, extend=0.1, N=200):
+    """src/DualTree01.jl:552-556 (v[1], v[2] are linear indices into the d x 2 range matrix, as in the reference)."""
+    v = getKDERange(bd, extend).ravel(order="F")
+    return np.linspace(v[0], v[1], N)
+
+
+def getKDEMax(p, N=200):
+    """src/DualTree01.jl:558-569: per-dimension argmax of the marginal on an N-point grid."""
+    m = np.zeros(Ndim(p))
+    for i in range(Ndim(p)):
+        mm = marginal(p, [i + 1])
+        r = getKDERange(mm).ravel(order="F")
+        X = np.linspace(r[0], r[1], N)
+        yV = mm(X.reshape(1, N))
+        m[i] = X[int(np.argmax(yV))]
+    return m
+
+
+def getKDEMean(p):
+    """src/DualTree01.jl:571-574"""
+    return getPoints(p).mean(axis=1)
+
+
+def getKDEfit(p):
+    """src/DualTree01.jl:575-578 with distribution=MvNormal: maximum-likelihood (mean, covariance)."""
+    pts = getPoints(p)
+    mu = pts.mean(axis=1)
+    c = (pts - mu[:, None]) @ (pts - mu[:, None]).T / pts.shape[1]
+    return mu, c
+
+
+def intersIntgAppxIS(p, q, N=201):
+    """src/DualTree01.jl:581-618: grid approximation of the integral of p*q (1-D and 2-D only)."""
+    nd = Ndim(p)
+    if nd > 2:
+        raise KDEError("Can't do higher dimensions yet")
+    LD = [getKDERangeLinspace(marginal(p, [k + 1]), N=N, extend=0.3) for k in range(nd)]
+    dx = [ld[1] - ld[0] for ld in LD]
+    xx = np.zeros((nd, N))
+    xx[0, :] = LD[0]
+    if nd == 1:
+        yy = evaluateDualTree(p, xx) * evaluateDualTree(q, xx)
+        return float(np.sum(yy) * dx[0])
+    acc = 0.0
+    for i in range(N):
+        xx[1, :] = LD[1][i]
+        yy = evaluateDualTree(p, xx) * evaluateDualTree(q, xx)
+        acc += (dx[0] * float(np.sum(yy))) * dx[1]
+    return acc
+
+
+def to_string(d):
+    """Base.string(::BallTreeDensity) (src/StringSerialization.jl:1-5): "KDE:N:[bw]:[pts]" """
+    pts = getPoints(d)
+    bw = getBW(d)[:, 0]
+    rows = ["%s" % " ".join(repr(float(v)) for v in row) for row in pts]
+    return "KDE:%d:[%s]:[%s]" % (pts.shape[1], ", ".join(repr(float(v)) for v in bw), "; ".join(rows))
+
+
+def from_string(text):
+    """convert(BallTreeDensity, ::String) (src/StringSerialization.jl:13-26)"""
+    if "KDE:" not in text:
+        raise KDEError("not a KDE string")
+    parts = [t.strip() for t in text.split(":")]
+    N = int(parts[1])
+    vec = lambda t, sep: [float(x) for x in t.strip().split("[")[-1].split("]")[0].split(sep) if x.strip()]
+    bw = vec(parts[2], ",")
+    rows = parts[3].split(";")
+    if len(rows) != len(bw):
+        raise KDEError("KDE string: %d bandwidths but %d point rows" % (len(bw), len(rows)))
+    pts = np.zeros((len(bw), N))
+    for i, r in enumerate(rows):
+        pts[i, :] = vec(r, None)
+    return kde(pts, bw)
+
+
 # ------------------------------------------------------------------------- LOOCV -------------
 def updateBandwidth(bd, bw):
     """updateBandwidth! (src/CrossValidation.jl:5-12).  The device copy is NOT re-uploaded: the
@@ -491,8 +586,9 @@ def prodAppxMSGibbsS(npd0, trees, anFcns=None, anParams=None, Niter=3, addop=Non
     return points.T, indices.T
 
 
-def prod(trees, glbs=None, addEntropy=True, seed=None):
-    """*(trees::Vector{BallTreeDensity}) (src/MSGibbs01.jl:707-726)"""
+def prod(trees, glbs=None, addEntropy=True, seed=None, recordLabels=False):
+    """*(trees::Vector{BallTreeDensity}) (src/MSGibbs01.jl:707-726).  recordLabels=True mirrors
+    `glbs.recordChoosen = true` (examples/ExtractingLabels.jl) and returns (density, labelsChoosen)."""
     trees = list(trees)
     if len(trees) == 1 and not addEntropy:
         return kde(getPoints(trees[0]).copy())
@@ -501,8 +597,9 @@ def prod(trees, glbs=None, addEntropy=True, seed=None):
     for p in trees:
         if d != Ndim(p):
             raise KDEError("kdes must have same dimension")
-    pGM, _ = prodAppxMSGibbsS(None, trees, None, None, Niter=5, addEntropy=addEntropy, Np=numpts, seed=seed)
-    return kde(pGM)
+    res = prodAppxMSGibbsS(None, trees, None, None, Niter=5, addEntropy=addEntropy, Np=numpts, seed=seed,
+                           recordLabels=recordLabels)
+    return (kde(res[0]), res[2]) if recordLabels else kde(res[0])
 
 
 # ------------------------------------------------------------------------- measurement -------

@@ -89,3 +89,20 @@ def test_header_is_plain_c(tmp_path):
                    '  return kdeb200_device_count(&n) == 0 ? kdeb200_version() - kdeb200_version() : 0; }\n')
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
                            "-c", str(src), "-o", str(tmp_path / "use.o")])
+
+
+def test_host_wrappers_without_device(built):
+    """String round trip (test/runtests.jl:246-255), ranges, mean, fit: pure host code."""
+    import kde_b200 as K
+    rng = np.random.default_rng(2)
+    p = K.kde(rng.standard_normal((2, 3)), [0.3, 0.4])
+    pp = K.from_string(K.to_string(p))
+    assert np.linalg.norm(K.getPoints(pp) - K.getPoints(p)) < 1e-4 and np.linalg.norm(K.getBW(pp) - K.getBW(p)) < 1e-4
+    r = K.getKDERange(p, extend=0.1)
+    pts = K.getPoints(p)
+    assert np.allclose(r[:, 0], pts.min(1) - 0.1 * (pts.max(1) - pts.min(1)))
+    assert np.allclose(K.getKDEMean(p), pts.mean(1))
+    mu, c = K.getKDEfit(p)
+    assert np.allclose(mu, pts.mean(1)) and c.shape == (2, 2)
+    with pytest.raises(K.KDEError):
+        K.from_string("nope")

@@ -142,3 +142,25 @@ def test_full_size_c5_spot_check():
     fa = w[: N // 2].sum() / w.sum()
     mix = fa * K.evaluateDualTree(pa, pos[:, :2000]) + (1 - fa) * K.evaluateDualTree(pb, pos[:, :2000])
     assert relerr(K.evaluateDualTree(pw, pos[:, :2000]), mix) < 1e-11
+
+
+def test_host_wrappers_over_the_eval_seam():
+    """integralAppxUnitTests (test/runtests.jl:203-223) through the GPU path, plus getKDEMax / kld."""
+    rng = np.random.default_rng(17)
+
+    def offs(o, dim=1, N=201):
+        p = K.kde(rng.standard_normal((dim, 100)))
+        pts = rng.standard_normal((dim, 150))
+        pts[0, :] += o
+        return K.intersIntgAppxIS(p, K.kde(pts), N=N)
+
+    assert 0.2 < offs(0.0) < 0.35
+    assert 0.1 < offs(1.0, N=1000) < 0.3
+    assert 0.01 < offs(-2.0, N=1000) < 0.17
+    assert 0.05 < offs(0.0, dim=2, N=101) < 0.15
+    p = K.kde(3.0 + 0.5 * rng.standard_normal((2, 400)))
+    assert np.all(np.abs(K.getKDEMax(p) - 3.0) < 0.5)
+    q = K.kde(3.5 + 0.5 * rng.standard_normal((2, 400)))
+    o_p, o_q = OKDE.kde_bw(K.getPoints(p), K.getBW(p)[:, 0]), OKDE.kde_bw(K.getPoints(q), K.getBW(q)[:, 0])
+    exp = o_p.eval_avg_logl(o_p) - o_q.eval_avg_logl(o_p)
+    assert abs(K.kld(p, q) - exp) < 1e-10 * abs(exp) and K.minkld(p, q) > 0

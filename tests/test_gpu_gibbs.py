@@ -206,3 +206,14 @@ def test_full_size_c4_properties():
     for s in range(0, 4096, 97):
         mus = np.stack([pts[j][:, qi[j, s] - 2] for j in range(8)])
         assert np.allclose(q[:, s], (lam * mus).sum(0) / lam.sum(0), rtol=1e-12, atol=1e-14)
+
+
+def test_extracting_labels_example():
+    """examples/ExtractingLabels.jl: with addEntropy=false each product point is the mean of the three
+    selected kernel means, recoverable from the recorded labels of the last level."""
+    X = [K.kde(np.array([[1.0, 2, 3]]), [1.0]), K.kde(np.array([[0.5, 1.5, 2.5]]), [1.0]), K.kde(np.array([[4.0, 5, 6]]), [1.0])]
+    # LOOCV of the 3 product points is degenerate; take the raw samples instead of kde!(pGM)
+    pts, ind, lab = K.prodAppxMSGibbsS(None, X, None, None, Niter=5, Np=3, addEntropy=False, seed=3, recordLabels=True)
+    for s in range(3):
+        mu = np.mean([K.getPoints(X[j])[0, lab[s, j, -1] - 1] for j in range(3)])
+        assert abs(pts[0, s] - mu) < 1e-13
