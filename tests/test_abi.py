@@ -106,3 +106,32 @@ def test_host_wrappers_without_device(built):
     assert np.allclose(mu, pts.mean(1)) and c.shape == (2, 2)
     with pytest.raises(K.KDEError):
         K.from_string("nope")
+
+
+def _build_c_example(tmp_path, built):
+    import subprocess
+    exe = tmp_path / "product_c"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "product_c.c"), "-o", str(exe),
+                           "-L", os.path.dirname(built.SO_PATH), "-lkdeb200", "-lm",
+                           "-Wl,-rpath," + os.path.dirname(built.SO_PATH)])
+    return exe
+
+
+def test_c_example_links_against_the_abi(built, tmp_path):
+    """examples/product_c.c: plain C99 against include/kdeb200.h + libkdeb200.so (no Python / torch)."""
+    import subprocess
+    import torch
+    exe = _build_c_example(tmp_path, built)
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert r.returncode in (1, 2) and "no CUDA" in (r.stderr + r.stdout) or "cuda" in (r.stderr + r.stdout).lower()
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_gpu(built, tmp_path):
+    import subprocess
+    exe = _build_c_example(tmp_path, built)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "product mean" in r.stdout
