@@ -1,9 +1,9 @@
 """Secondary workloads of BASELINE.json (parity-test cases with timings, not the bench line):
   C5: brute-force evaluation of a 1M-component 3-D KDE at 1M query points (FP64 and FP32)
   C3: kde! LOOCV bandwidth selection on 100k synthetic 4-D mixture points (FP64)
-usage: python tools/bench_eval.py [c5] [c3] [--small]"""
+usage: python tests/perf/bench_eval.py [c5] [c3] [--small]"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import kde_b200 as K
 from tests.util import mixture, silverman

@@ -1,7 +1,7 @@
 """BASELINE configs 1 and 2 (the reference's own CPU-sized cases): GPU wall time per call next to the
-oracle port on one thread.  usage: python tools/bench_small.py"""
+oracle port on one thread.  usage: python tests/perf/bench_small.py"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import kde_b200 as K
 from oracle import oracle as O

@@ -1,8 +1,8 @@
 """Label parity at scale: C4-shaped product, injected Philox streams, GPU vs the oracle
 (OpenMP over chains).  Reports the number of samples whose label vector differs.
-usage: python tools/label_parity_scale.py [samples]"""
+usage: python tests/perf/label_parity_scale.py [samples]"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import kde_b200 as K
 from oracle import oracle as O
