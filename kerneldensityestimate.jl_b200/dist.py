@@ -40,6 +40,17 @@ def _world(group=None):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
+def _exchange_device(device=None, group=None):
+    """Where exchange tensors live: the caller's choice, else CUDA under NCCL and host under gloo."""
+    import torch
+    if device is not None:
+        return device
+    dist = _dist()
+    if dist.is_initialized() and dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
 def all_gather_blocks(local, n_total, group=None):
     """Assemble per-rank row blocks (shard_range order) into the full array on every rank.
     `local` is a torch tensor [n_local, ...] on the backend's device; uneven blocks are padded."""
@@ -77,7 +88,7 @@ def prod_sharded(trees, Np, Niter=5, seed=0, addEntropy=True, partialDimMask=Non
     pts, idx = compute(s0, s1)
     if world == 1:
         return pts, idx
-    dev = torch.device("cpu") if device is None else device
+    dev = _exchange_device(device, group)
     tp = torch.from_numpy(np.ascontiguousarray(pts.T)).to(dev)   # [n, d]
     ti = torch.from_numpy(np.ascontiguousarray(idx.T)).to(dev)   # [n, M]
     gp = all_gather_blocks(tp, Np, group).cpu().numpy()
@@ -115,7 +126,7 @@ def eval_sharded(bd, pos, group=None, compute=None, device=None):
     p = np.asarray(compute(a, b), dtype=np.float64)
     if world == 1:
         return p
-    dev = torch.device("cpu") if device is None else device
+    dev = _exchange_device(device, group)
     return all_gather_blocks(torch.from_numpy(p).to(dev), M, group).cpu().numpy()
 
 
@@ -134,7 +145,7 @@ def loo_entropy_sharded(bd, bw_var=None, group=None, compute=None, device=None, 
             return s.value, f.value
     s, f = compute(a, b)
     if world > 1:
-        dev = torch.device("cpu") if device is None else device
+        dev = _exchange_device(device, group)
         ts = torch.tensor([s], dtype=torch.float64, device=dev)
         tf = torch.tensor([int(f)], dtype=torch.int32, device=dev)
         dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=group)
