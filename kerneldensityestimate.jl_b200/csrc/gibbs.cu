@@ -160,14 +160,18 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
 
   Draw *d_draws = nullptr;
   TileDesc *d_tiles = nullptr;
+  int *d_counter = nullptr;
   KDE_CUDA(cudaMallocAsync(&d_draws, sizeof(Draw) * S.draws.size(), st));
   KDE_CUDA(cudaMallocAsync(&d_tiles, sizeof(TileDesc) * S.tiles.size(), st));
+  KDE_CUDA(cudaMallocAsync(&d_counter, 256, st));
+  KDE_CUDA(cudaMemsetAsync(d_counter, 0, 256, st));
   KDE_CUDA(cudaMemcpyAsync(d_draws, S.draws.data(), sizeof(Draw) * S.draws.size(), cudaMemcpyHostToDevice, st));
   KDE_CUDA(cudaMemcpyAsync(d_tiles, S.tiles.data(), sizeof(TileDesc) * S.tiles.size(), cudaMemcpyHostToDevice, st));
   KDE_CUDA(cudaStreamSynchronize(st));  // S's vectors are pageable host memory
 
   P.draws = d_draws;
   P.tiles = d_tiles;
+  P.counter = d_counter;
   P.exptab = c.d_exptab;
   P.ec = make_exp_consts();
   P.randU = d_randU;
@@ -213,6 +217,7 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
   if (launches) *launches += 1;
   KDE_CUDA(cudaFreeAsync(d_draws, st));
   KDE_CUDA(cudaFreeAsync(d_tiles, st));
+  KDE_CUDA(cudaFreeAsync(d_counter, st));
   return 0;
 }
 

@@ -79,6 +79,7 @@ struct alignas(16) TileDesc {
 struct GibbsParams {
   const Draw *draws;
   const TileDesc *tiles;
+  int *counter;  // batch counter of this launch (zeroed before the launch)
   const double *exptab;
   ExpConsts ec;
   const double *randU, *randN;  // injected streams or null (Philox)
@@ -214,8 +215,10 @@ struct Ring {
   double *tiles;
   uint64_t *bars;
   const TileDesc *descs;
-  int64_t total;  // tiles this CTA will consume over its whole life
-  int ntiles;     // tiles per sample schedule
+  int64_t known;   // tiles of the batches this CTA has claimed so far (current + one look-ahead): the producer
+                   // may prefetch up to here; grows by ntiles whenever another batch is claimed
+  int64_t issued;  // tiles handed to the TMA unit so far (meaningful in thread 0 only)
+  int ntiles;      // tiles per sample schedule
 };
 
 __device__ __forceinline__ void ring_issue(const Ring &R, int64_t q) {
@@ -223,6 +226,15 @@ __device__ __forceinline__ void ring_issue(const Ring &R, int64_t q) {
   uint64_t *bar = &R.bars[q % GB_STAGES];
   mbar_expect_tx(bar, td.bytes);
   tma_bulk_g2s(R.tiles + (size_t)(q % GB_STAGES) * (GB_TILE_BYTES / 8), td.src, td.bytes, bar);
+}
+
+// thread 0: keep the ring GB_STAGES tiles ahead of the `consumed` tiles, never past the claimed batches.
+// Stage issued % GB_STAGES is free once tile issued - GB_STAGES has been consumed.
+__device__ __forceinline__ void ring_fill(Ring &R, int64_t consumed) {
+  while (R.issued < R.known && R.issued < consumed + GB_STAGES) {
+    ring_issue(R, R.issued);
+    ++R.issued;
+  }
 }
 
 // consume one pipelined group: p = exp(arg)[*sc], sequential adds
@@ -238,7 +250,7 @@ __device__ __forceinline__ void consume_group(const double (&arg)[UNR], const do
 
 template <int D, bool MASK, int VAR>
 __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h, const double *__restrict__ tab,
-                                        const ExpConsts &ec, const Ring &R, int64_t &q, double *__restrict__ ck) {
+                                        const ExpConsts &ec, Ring &R, int64_t &q, double *__restrict__ ck) {
   // UNR nodes per group.  Within a tile the groups are software-pipelined with two register sets
   // (A/B ping-pong, no rotation moves): stage 1 (record -> exponent) of group g is issued in the
   // same basic block as the exp chains of group g-1.  Fewer nodes per group at high d, where ptxas
@@ -285,7 +297,7 @@ __device__ __forceinline__ double pass1(const Draw &dr, const Hoist<D, MASK> &h,
       if ((consumed & (G - 1)) == 0 || consumed == n) ck[c++] = S;
     }
     __syncthreads();  // stage free again
-    if (threadIdx.x == 0 && q + GB_STAGES < R.total) ring_issue(R, q + GB_STAGES);
+    if (threadIdx.x == 0) ring_fill(R, q + 1);
   }
   return S;
 }
@@ -327,16 +339,22 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
   }
   __syncthreads();
 
-  int nb_local = 0;
-  for (int b = blockIdx.x; b < P.nbatches; b += gridDim.x) ++nb_local;
+  // Dynamic batch scheduling: CTAs claim batches of 128 chains from a global counter.  The next batch is
+  // claimed at the start of the LAST draw of the current one (late, so that no CTA hoards work, but early
+  // enough for the tile ring to prefetch across the batch boundary).  Chains are addressed by sample index,
+  // so the result does not depend on which CTA runs which batch.
+  __shared__ int claim;
+  if (tid == 0) claim = atomicAdd(P.counter, 1);
+  __syncthreads();
+  int batch = claim, batch_next = P.nbatches;
   Ring R;
   R.tiles = tiles;
   R.bars = bars;
   R.descs = P.tiles;
   R.ntiles = P.ntiles;
-  R.total = (int64_t)nb_local * P.ntiles;
-  if (tid == 0)
-    for (int64_t q0 = 0; q0 < GB_STAGES && q0 < R.total; ++q0) ring_issue(R, q0);
+  R.known = (batch < P.nbatches) ? P.ntiles : 0;
+  R.issued = 0;
+  if (tid == 0) ring_fill(R, 0);
   int64_t q = 0;
 
   // chain state: lambda = 1/variance and lambda*mu of the currently selected node of each density
@@ -345,7 +363,7 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
   double ck[GB_MAXCK];
   int selpos[KDEB200_MAX_DENS];
 
-  for (int batch = blockIdx.x; batch < P.nbatches; batch += gridDim.x) {
+  while (batch < P.nbatches) {
     int64_t s = P.s0 + (int64_t)batch * GB_THREADS + tid;
     const bool live = s < P.s1;
     if (!live) s = P.s1 - 1;  // idle lanes replay the last chain (keeps the CTA in lock-step)
@@ -371,6 +389,13 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
     for (int di = 0; di < P.ndraws; ++di) {
       const Draw dr = P.draws[di];
       const int j = dr.j;
+      if (di == P.ndraws - 1) {  // claim the next batch (uniform branch; two barriers around the shared word)
+        __syncthreads();
+        if (tid == 0) claim = atomicAdd(P.counter, 1);
+        __syncthreads();
+        batch_next = claim;
+        if (batch_next < P.nbatches) R.known += P.ntiles;
+      }
 
       if (dr.new_level) {  // samplePoint!(addEntropy = true) with normals g(level-1, k)
 #pragma unroll
@@ -532,6 +557,8 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
         P.points[o * D + k] = v;
       }
     }
+
+    batch = batch_next;
   }
 }
 
