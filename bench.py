@@ -37,6 +37,7 @@ SAMPLES_PER_GPU = 1_000_000
 # algorithmic FP64-pipe slots per sample for this shape: 393216 leaf-level
 # evaluations x 22 + 196512 internal-level evaluations x 47
 ALG_SLOTS_PER_SAMPLE = 393216 * 22 + 196512 * 47
+ISSUED_FP64_PER_SAMPLE = 31035518826 * 32 / 75776  # executed DFMA+DMUL+DADD warp-instructions x 32 lanes / samples (ncu)
 
 
 def synth_points(j):
@@ -284,6 +285,11 @@ def main():
                                 "dram read 0.26 GB + write 2.76 GB (local-memory checkpoints leaving L2), i.e. ~40 KB/sample "
                                 "or <0.5% of HBM bandwidth; a full 1M-sample launch does not finish under ncu replay",
                 "kernel": "gibbs_kernel<3,false>", "kernel_ms": k_ms,
+                # honest "issued" view next to the algorithmic one (SURVEY.md 8d asks for both): the kernel issues
+                # 13.1e6 FP64 instructions per sample (ncu, profiles/r01_gibbs_v8_ncu.txt) -- fewer than the model's
+                # 17.9e6 slots because exp costs 7 instructions instead of 14 -- so frac can exceed 1
+                "issued_fp64_instr_per_sample": ISSUED_FP64_PER_SAMPLE,
+                "issued_frac": ISSUED_FP64_PER_SAMPLE * n_per / (k_ms * 1e-3) / dfma,
                 "algorithmic_fp64_slots_per_sample": ALG_SLOTS_PER_SAMPLE, "kernel_evals_per_sample": evals,
                 "peak_source": "DFMA microbenchmark (kdeb200_pipe_peak) measured in this run; nominal 64/clk/SM x 148 x 1.965 GHz = 37.2 TFLOP/s",
                 "note": "path is FP64-FMA-pipe bound, not HBM/tensor (SURVEY.md 8d); HBM peak of MEASURED_PEAKS.json = %s GB/s unused" % peaks_file.get("hbm_gbs")}
