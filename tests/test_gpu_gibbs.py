@@ -217,3 +217,12 @@ def test_extracting_labels_example():
     for s in range(3):
         mu = np.mean([K.getPoints(X[j])[0, lab[s, j, -1] - 1] for j in range(3)])
         assert abs(pts[0, s] - mu) < 1e-13
+
+
+@pytest.mark.parametrize("M,N,T,Np", [(1, 1, 0, 5000), (1, 2, 1, 4097), (2, 2, 0, 3000), (2, 3, 1, 2500), (3, 5, 0, 129)])
+def test_many_batches_tiny_schedules(M, N, T, Np):
+    """Dynamic batch scheduling with schedules of only a few tiles per batch (the tile ring's look-ahead
+    crosses batch boundaries constantly) and sample counts that are not multiples of the CTA size."""
+    rng = np.random.default_rng(M * 100 + N * 10 + T)
+    pairs = [make(rng, 2, N, 0.5 * j, bw=np.array([0.5, 0.7])) for j in range(M)]
+    compare([p[0] for p in pairs], [p[1] for p in pairs], Np, T, rng)
