@@ -55,6 +55,12 @@ int kdeb200_device_props(int *sm_count, int *cc_major, int *cc_minor, int *clock
 int kdeb200_tree_create(int d, int64_t N, const double *means, const double *bandwidth, const double *weights,
                         const int64_t *left_child, const int64_t *right_child, const int64_t *permutation,
                         kdeb200_tree_t *out);
+/* Evaluation-only hand-over: uploads the leaf records alone (8*(d+2)*N bytes instead of the
+ * ~5x larger level records), for trees that only meet kdeb200_eval* / kdeb200_loo_* -- e.g. the
+ * marginals that nLOO_LL / ksize (src/CrossValidation.jl:15-24, 65-83) build once per dimension.
+ * A Gibbs call on such a handle fails with code 7. */
+int kdeb200_tree_create_eval(int d, int64_t N, const double *means, const double *bandwidth,
+                             const double *weights, const int64_t *permutation, kdeb200_tree_t *out);
 int kdeb200_tree_destroy(kdeb200_tree_t t);
 int kdeb200_tree_info(kdeb200_tree_t t, int *d, int64_t *N, int *nlevels, int64_t *device_bytes);
 

@@ -27,16 +27,23 @@ init(device::Integer=0) = check(ccall((:kdeb200_init, LIB), Cint, (Cint,), devic
 # ---- S0: device-resident BallTreeDensity -------------------------------------------------
 mutable struct DeviceTree
   h::Ptr{Cvoid}
-  function DeviceTree(bd::BallTreeDensity)
+  # gibbs=false: leaf records only (evaluate / entropy / nLOO_LL never touch the level records)
+  function DeviceTree(bd::BallTreeDensity; gibbs::Bool=true)
     bd.multibandwidth == 0 || error("kdeb200: multibandwidth != 0 is not supported")
     bt = bd.bt
     out = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve bd begin
-      check(ccall((:kdeb200_tree_create, LIB), Cint,
-                  (Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64},
-                   Ref{Ptr{Cvoid}}),
-                  bt.dims, bt.num_points, bd.means, bd.bandwidth, bt.weights, bt.left_child, bt.right_child,
-                  bt.permutation, out))
+      if gibbs
+        check(ccall((:kdeb200_tree_create, LIB), Cint,
+                    (Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64},
+                     Ref{Ptr{Cvoid}}),
+                    bt.dims, bt.num_points, bd.means, bd.bandwidth, bt.weights, bt.left_child, bt.right_child,
+                    bt.permutation, out))
+      else
+        check(ccall((:kdeb200_tree_create_eval, LIB), Cint,
+                    (Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+                    bt.dims, bt.num_points, bd.means, bd.bandwidth, bt.weights, bt.permutation, out))
+      end
     end
     t = new(out[])
     finalizer(x -> ccall((:kdeb200_tree_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), t)
@@ -80,7 +87,7 @@ function evaluate!(bd::BallTreeDensity, locations::BallTreeDensity, p::Vector{Fl
                    maxErr::Float64=1e-3, addop=(+,), diffop=(-,); precision::Int=0)
   bd.bt.dims == locations.bt.dims || error("evaluate -- dimensions of two BallTreeDensities must match")
   euclidean(addop, diffop) || error("kdeb200: only the default Euclidean (+,-) manifold is supported")
-  dt = DeviceTree(bd)
+  dt = DeviceTree(bd; gibbs=false)
   if bd === locations
     GC.@preserve dt p check(ccall((:kdeb200_eval, LIB), Cint,
       (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Cint, Ptr{Float64}), dt.h, C_NULL, Npts(bd), 1, precision, p))
@@ -94,7 +101,7 @@ end
 
 function evaluateDualTree(bd::BallTreeDensity, pos::Matrix{Float64}, lvFlag::Bool=false; precision::Int=0)
   bd.bt.dims == size(pos, 1) || error("bd and pos must have the same dimension")
-  dt = DeviceTree(bd)
+  dt = DeviceTree(bd; gibbs=false)
   M = lvFlag ? Npts(bd) : size(pos, 2)
   p = zeros(M)
   GC.@preserve dt pos p check(ccall((:kdeb200_eval, LIB), Cint,
@@ -103,7 +110,7 @@ function evaluateDualTree(bd::BallTreeDensity, pos::Matrix{Float64}, lvFlag::Boo
 end
 
 # ---- S3: leave-one-out entropy (one launch, one scalar back) ------------------------------------
-function entropy(bd::BallTreeDensity, dt::DeviceTree=DeviceTree(bd))
+function entropy(bd::BallTreeDensity, dt::DeviceTree=DeviceTree(bd; gibbs=false))
   H = Ref{Float64}(0.0)
   bw = bd.bandwidthMin[1:bd.bt.dims]     # the (possibly alpha^2-scaled) leaf variances
   GC.@preserve dt bw check(ccall((:kdeb200_loo_entropy, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}),

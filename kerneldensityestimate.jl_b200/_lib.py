@@ -22,6 +22,7 @@ SIGNATURES = {
     "kdeb200_shutdown": (C.c_int, []),
     "kdeb200_device_props": (C.c_int, [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_size_t)]),
     "kdeb200_tree_create": (C.c_int, [C.c_int, C.c_int64, f64p, f64p, f64p, i64p, i64p, i64p, C.POINTER(tree_t)]),
+    "kdeb200_tree_create_eval": (C.c_int, [C.c_int, C.c_int64, f64p, f64p, f64p, i64p, C.POINTER(tree_t)]),
     "kdeb200_tree_destroy": (C.c_int, [tree_t]),
     "kdeb200_tree_info": (C.c_int, [tree_t, C.POINTER(C.c_int), i64p, C.POINTER(C.c_int), i64p]),
     "kdeb200_tree_build_host": (C.c_int, [C.c_int, C.c_int64, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p,

@@ -80,16 +80,27 @@ class BallTreeDensity:
         self.bandwidthMin = bandwidth[N * d:].copy()
         self.bandwidthMax = bandwidth[N * d:].copy()
         self._handle = None
+        self._handle_gibbs = False
 
     # -- device residency --------------------------------------------------------------
-    def _dev(self):
+    def _dev(self, gibbs=False):
+        """Device handle; evaluation / LOOCV callers get the leaf-only hand-over
+        (kdeb200_tree_create_eval), the first Gibbs use upgrades it to the full level records."""
+        if self._handle is not None and gibbs and not self._handle_gibbs:
+            self._invalidate()
         if self._handle is None:
             h = _lib.tree_t()
             bt = self.bt
-            check(lib().kdeb200_tree_create(bt.dims, bt.num_points, fptr(self.means), fptr(self.bandwidth),
-                                            fptr(bt.weights), iptr(bt.left_child), iptr(bt.right_child),
-                                            iptr(bt.permutation), C.byref(h)))
+            if gibbs:
+                check(lib().kdeb200_tree_create(bt.dims, bt.num_points, fptr(self.means), fptr(self.bandwidth),
+                                                fptr(bt.weights), iptr(bt.left_child), iptr(bt.right_child),
+                                                iptr(bt.permutation), C.byref(h)))
+            else:
+                check(lib().kdeb200_tree_create_eval(bt.dims, bt.num_points, fptr(self.means),
+                                                     fptr(self.bandwidth), fptr(bt.weights),
+                                                     iptr(bt.permutation), C.byref(h)))
             self._handle = h
+            self._handle_gibbs = gibbs
         return self._handle
 
     def _invalidate(self):
@@ -511,7 +522,7 @@ def ksize(bd, addop=None, diffop=None, _count=None):
 def _handles(trees):
     arr = (_lib.tree_t * len(trees))()
     for i, t in enumerate(trees):
-        arr[i] = t._dev()
+        arr[i] = t._dev(gibbs=True)
     return arr
 
 

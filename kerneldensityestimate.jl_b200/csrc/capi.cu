@@ -13,7 +13,8 @@ int tree_build_host(int d, int64_t N, const double *points, const double *weight
                     double *centers, double *ranges, double *wout, double *means, double *bandwidth,
                     int64_t *left, int64_t *right, int64_t *lowest, int64_t *highest, int64_t *perm);
 int tree_create(int d, int64_t N, const double *means, const double *bandwidth, const double *weights,
-                const int64_t *left, const int64_t *right, const int64_t *perm, kdeb200_tree_t *out);
+                const int64_t *left, const int64_t *right, const int64_t *perm, bool gibbs_records,
+                kdeb200_tree_t *out);
 int tree_destroy(kdeb200_tree_t t);
 int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int64_t q0, bool scatter,
                 const double *bw_var, double *d_out, cudaStream_t st, int *launches);
@@ -87,7 +88,14 @@ int kdeb200_tree_create(int d, int64_t N, const double *means, const double *ban
   KDE_SERIALISE();
   if (!means || !bandwidth || !weights || !left_child || !right_child || !permutation)
     KDE_FAIL(2, "tree_create: NULL argument");
-  return tree_create(d, N, means, bandwidth, weights, left_child, right_child, permutation, out);
+  return tree_create(d, N, means, bandwidth, weights, left_child, right_child, permutation, true, out);
+}
+
+int kdeb200_tree_create_eval(int d, int64_t N, const double *means, const double *bandwidth, const double *weights,
+                             const int64_t *permutation, kdeb200_tree_t *out) {
+  KDE_SERIALISE();
+  if (!means || !bandwidth || !weights || !permutation) KDE_FAIL(2, "tree_create_eval: NULL argument");
+  return tree_create(d, N, means, bandwidth, weights, nullptr, nullptr, permutation, false, out);
 }
 
 int kdeb200_tree_destroy(kdeb200_tree_t t) {

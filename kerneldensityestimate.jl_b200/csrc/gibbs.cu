@@ -105,6 +105,8 @@ int gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels,
   if (Niter < 0) KDE_FAIL(3, "gibbs: Niter must be >= 0");
   for (int j = 0; j < ndens; ++j) {
     if (!trees[j]) KDE_FAIL(3, "gibbs: tree %d is NULL", j);
+    if (!trees[j]->gibbs_ready)
+      KDE_FAIL(7, "gibbs: tree %d was created by kdeb200_tree_create_eval (leaf records only); use kdeb200_tree_create", j);
     if (trees[j]->d != trees[0]->d) KDE_FAIL(6, "kdes must have same dimension");  // src/MSGibbs01.jl:721
   }
   const int L = gibbs_nlevels(trees, ndens);

@@ -173,7 +173,8 @@ int tree_build_host(int d, int64_t N, const double *points, const double *weight
 static inline int even_up(int x) { return (x + 1) & ~1; }
 
 int tree_create(int d, int64_t N, const double *means, const double *bandwidth, const double *weights,
-                const int64_t *left, const int64_t *right, const int64_t *perm, kdeb200_tree_t *out) {
+                const int64_t *left, const int64_t *right, const int64_t *perm, bool gibbs_records,
+                kdeb200_tree_t *out) {
   if (int rc = ensure_init()) return rc;
   if (!out) KDE_FAIL(2, "tree_create: out is NULL");
   if (d < 1 || d > KDEB200_MAX_DIM) KDE_FAIL(3, "tree_create: d=%d outside 1..%d (no CPU fallback)", d, KDEB200_MAX_DIM);
@@ -198,10 +199,11 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
         KDE_FAIL(4, "tree_create: per-point bandwidths (multibandwidth != 0) are not supported");
       }
 
-  // BFS level lists exactly as levelDown! produces them (left then right, leaves persist)
+  // BFS level lists exactly as levelDown! produces them (left then right, leaves persist); an
+  // evaluation-only tree (kdeb200_tree_create_eval) carries the leaf records alone
   std::vector<std::vector<int64_t>> lists;
-  lists.push_back({1});
-  for (;;) {
+  if (gibbs_records) lists.push_back({1});
+  while (gibbs_records) {
     const std::vector<int64_t> &cur = lists.back();
     std::vector<int64_t> nxt;
     nxt.reserve(cur.size() * 2);
@@ -217,7 +219,9 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
     }
     lists.push_back(std::move(nxt));
   }
-  t->depth = (int)lists.size() - 1;
+  t->gibbs_ready = gibbs_records;
+  t->depth = gibbs_records ? (int)lists.size() - 1 : 0;
+  if (gibbs_records)
   for (int64_t y : lists.back())
     if (y <= N) {
       delete t;
@@ -282,7 +286,7 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
 
   // leaf-order evaluation records and labels
   std::vector<double> leaf((size_t)N * t->SE, 0.0);
-  std::vector<int64_t> pr(N), lab(lists.back().size());
+  std::vector<int64_t> pr(N), lab(gibbs_records ? lists.back().size() : 0);
   for (int64_t s = 0; s < N; ++s) {
     const int64_t node = N + s;
     for (int k = 0; k < d; ++k) leaf[s * t->SE + k] = means[node * d + k];

@@ -24,6 +24,7 @@ struct Level {
 struct kdeb200_tree_s {
   int d = 0;
   int64_t N = 0;
+  bool gibbs_ready = false; // level records present (kdeb200_tree_create); false for kdeb200_tree_create_eval
   bool degenerate = false;  // some bandwidth <= 0 or non-finite value: fast arithmetic not valid
   double hvar[KDEB200_MAX_DIM] = {0};  // the uniform leaf variances (bandwidthMin/Max[1:d])
   double root_mean[KDEB200_MAX_DIM] = {0};  // mean of node 1 (centre of the FP32 coordinates)

@@ -164,3 +164,29 @@ def test_host_wrappers_over_the_eval_seam():
     o_p, o_q = OKDE.kde_bw(K.getPoints(p), K.getBW(p)[:, 0]), OKDE.kde_bw(K.getPoints(q), K.getBW(q)[:, 0])
     exp = o_p.eval_avg_logl(o_p) - o_q.eval_avg_logl(o_p)
     assert abs(K.kld(p, q) - exp) < 1e-10 * abs(exp) and K.minkld(p, q) > 0
+
+
+def test_eval_only_handle_then_gibbs_upgrade():
+    """kdeb200_tree_create_eval carries the leaf records alone: evaluation and LOOCV work on it, a Gibbs call is
+    refused (code 7), and the Python mirror upgrades the handle on its first Gibbs use with unchanged answers."""
+    import ctypes as C
+    from kde_b200 import _lib
+    rng = np.random.default_rng(77)
+    pts = mixture(rng, 3, 700)
+    p = K.kde(pts, [0.3, 0.2, 0.4])
+    q = rng.normal(size=(3, 50))
+    before = K.evaluateDualTree(p, q)
+    H0 = K.entropy(p)
+    assert not p._handle_gibbs
+    nb_eval = C.c_int64(0)
+    _lib.check(_lib.lib().kdeb200_tree_info(p._dev(), None, None, None, C.byref(nb_eval)))
+    arr = (_lib.tree_t * 1)(p._dev())
+    L = C.c_int(0)
+    rc = _lib.lib().kdeb200_gibbs_sizes(arr, 1, 3, C.byref(L), None, None, None)
+    assert rc == 7 and b"tree_create_eval" in _lib.lib().kdeb200_last_error()
+    pts_out, _ = K.prodAppxMSGibbsS(None, [p, p], None, None, Niter=2, Np=64, seed=5)[:2]
+    assert p._handle_gibbs and pts_out.shape == (3, 64)
+    nb_full = C.c_int64(0)
+    _lib.check(_lib.lib().kdeb200_tree_info(p._dev(), None, None, None, C.byref(nb_full)))
+    assert nb_full.value > 2 * nb_eval.value
+    assert np.array_equal(before, K.evaluateDualTree(p, q)) and H0 == K.entropy(p)
