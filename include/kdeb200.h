@@ -126,6 +126,16 @@ int kdeb200_loo_entropy(kdeb200_tree_t bd, const double *bw_var, double *H_out);
 int kdeb200_loo_partial(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int64_t j1, double *sum_out,
                         int *zero_flag_out);
 
+/* kde!(points) bandwidth selection in one call: the per-dimension loop of src/KDE01.jl:13-23,
+ *   bwds[i] = getBW(ksize(marginal(p, [i])))[1]
+ * i.e. marginal (src/KDE01.jl:143-153), neighborMinMax, ksize and golden over nLOO_LL
+ * (src/CrossValidation.jl:15-24, 44-120).  points is d x N column-major; bw_std_out receives the d
+ * standard deviations to hand to kde!(points, bwds); nloo_calls_out (d entries, may be NULL) the
+ * number of nLOO_LL evaluations per dimension.  N <= 512 runs every dimension's whole
+ * golden-section search in ONE kernel launch; larger N loops on the host over the tiled LOO
+ * kernel.  Both give the bits of the call-by-call route through kdeb200_loo_entropy. */
+int kdeb200_kde_lcv(int d, int64_t N, const double *points, double *bw_std_out, int *nloo_calls_out);
+
 /* ---- measurement ----------------------------------------------------------------------------
  * Pipe-rate microbenchmarks for the roofline denominators: dependent-free DFMA,
  * FFMA and MUFU.EX2 loops over the whole chip.  which: 0 = DFMA, 1 = FFMA, 2 = MUFU.EX2.

@@ -118,6 +118,15 @@ function entropy(bd::BallTreeDensity, dt::DeviceTree=DeviceTree(bd; gibbs=false)
   return H[]
 end
 
+# the bandwidth loop of kde!(points) (src/KDE01.jl:13-23) in one call; N <= 512: one kernel launch
+function lcv_bandwidths(points::Matrix{Float64})
+  d, N = size(points)
+  bw = zeros(d)
+  GC.@preserve points bw check(ccall((:kdeb200_kde_lcv, LIB), Cint,
+    (Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}), d, N, points, bw, C_NULL))
+  return bw
+end
+
 # nLOO_LL with the device tree reused across the ~20 golden-section steps of one ksize call
 function nLOO_LL(alpha::Float64, bd::BallTreeDensity, dt::DeviceTree)
   a2 = alpha^2

@@ -38,6 +38,7 @@ SIGNATURES = {
     "kdeb200_eval_device": (C.c_int, [tree_t, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "kdeb200_loo_entropy": (C.c_int, [tree_t, f64p, f64p]),
     "kdeb200_loo_partial": (C.c_int, [tree_t, f64p, C.c_int64, C.c_int64, f64p, C.POINTER(C.c_int)]),
+    "kdeb200_kde_lcv": (C.c_int, [C.c_int, C.c_int64, f64p, f64p, C.POINTER(C.c_int)]),
     "kdeb200_pipe_peak": (C.c_int, [C.c_int, C.c_int, f64p, f64p]),
     "kdeb200_dfma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, f64p]),
     "kdeb200_last_kernel_ms": (C.c_int, [f64p, C.POINTER(C.c_int)]),

@@ -28,7 +28,7 @@ from ._lib import KDEError, check, fptr, iptr, lib
 __all__ = [
     "KDEError", "BallTree", "BallTreeDensity", "kde", "kde_bang", "getPoints", "getBW", "getWeights", "marginal",
     "sample", "rand", "resample", "evaluateDualTree", "evalAvgLogL", "entropy", "kld", "minkld", "nLOO_LL", "golden",
-    "ksize", "neighborMinMax", "updateBandwidth", "prodAppxMSGibbsS", "Ndim", "Npts", "init", "gibbs_sizes",
+    "ksize", "neighborMinMax", "lcv_bandwidths", "updateBandwidth", "prodAppxMSGibbsS", "Ndim", "Npts", "init", "gibbs_sizes",
     "philox_streams", "pipe_peak", "last_kernel_ms", "F64", "F32", "prod", "getKDERange", "getKDERangeLinspace",
     "getKDEMax", "getKDEMean", "getKDEfit", "intersIntgAppxIS", "to_string", "from_string",
 ]
@@ -163,15 +163,35 @@ def _make_ball_tree_density(points, weights, bwvar):
     return BallTreeDensity(bt, means, bandwidth)
 
 
-def kde(points, ks=None, weights=None, addop=None, diffop=None):
+def lcv_bandwidths(points, _count=None):
+    """The bandwidth loop of kde!(points) (src/KDE01.jl:13-23) behind ONE library call
+    (kdeb200_kde_lcv): per dimension marginal -> ksize -> golden over nLOO_LL, entirely native;
+    N <= 512 runs all golden-section searches in a single kernel launch.  Returns the d standard
+    deviations.  Bit-identical to the step-by-step mirror `kde(points, native_lcv=False)`."""
+    pts = _as_matrix(points)
+    d, N = pts.shape
+    flat = np.ascontiguousarray(pts.T).ravel()
+    bw = np.zeros(d)
+    calls = (C.c_int * d)()
+    check(lib().kdeb200_kde_lcv(d, N, fptr(flat), fptr(bw), calls))
+    if _count is not None:
+        _count.extend(int(c) for c in calls)
+    return bw
+
+
+def kde(points, ks=None, weights=None, addop=None, diffop=None, native_lcv=True):
     """kde!(points) / kde!(points, ks) / kde!(points, ks, weights)  (src/KDE01.jl:3-84).
 
     ks = None selects every dimension's bandwidth by leave-one-out likelihood cross validation
-    (the per-dimension `ksize(marginal(p,[i]))` loop of src/KDE01.jl:17-23)."""
+    (the per-dimension `ksize(marginal(p,[i]))` loop of src/KDE01.jl:17-23): in one native call
+    (lcv_bandwidths) or, with native_lcv=False, step by step through the mirrors of marginal /
+    ksize / golden / nLOO_LL (one kdeb200_loo_entropy call per golden-section step)."""
     _require_euclidean(addop=addop, diffop=diffop)
     pts = _as_matrix(points)
     d, N = pts.shape
     if ks is None:
+        if native_lcv:
+            return kde(pts, lcv_bandwidths(pts))
         p = kde(pts, [1.0])
         bwds = np.zeros(d)
         for i in range(d):

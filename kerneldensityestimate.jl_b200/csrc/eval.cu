@@ -12,6 +12,7 @@
 #include <cmath>
 #include <vector>
 
+#include "eval_shared.cuh"
 #include "tree.cuh"
 
 namespace kdeb200 {
@@ -59,26 +60,6 @@ __device__ __forceinline__ double quad(const double (&x)[D], const double (&r)[S
     acc = __fma_rn(__dmul_rn(df, df), ich[k], acc);
   }
   return acc;
-}
-
-// Rows whose fast-path total is below EV_TINY (density < 1e-275: the point is > 35 bandwidths away from
-// every component) are recomputed here with libdevice exp, sequentially in leaf order, so that
-// subnormal values and exact zeros (the likelihood's zero rule) match the reference.
-constexpr double EV_TINY = 1e-275;
-__device__ __noinline__ double exact_row(const double *__restrict__ comps, int SE, int D, int64_t N,
-                                         const double *__restrict__ xq, const double *__restrict__ ich, int64_t self) {
-  double s = 0.0;
-  for (int64_t i = 0; i < N; ++i) {
-    if (i == self) continue;
-    const double *r = comps + i * SE;
-    double acc = 0.0;
-    for (int k = 0; k < D; ++k) {
-      const double df = __dadd_rn(xq[k], -r[k]);
-      acc = __fma_rn(__dmul_rn(df, df), ich[k], acc);
-    }
-    s = __fma_rn(exp(acc), r[D], s);
-  }
-  return s;
 }
 
 template <int D, int Q, bool LOO>
@@ -222,24 +203,8 @@ __global__ void loglik_reduce_kernel(const double *L, const double *comps, int S
   __shared__ int shf[1024];
   double s = 0.0;
   int f = 0;
-  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-    const double l = L[j], w = comps[(q0 + j) * SE + D];
-    if (l == 0.0) {
-      if (w != 0.0) f = 1;
-    } else {
-      s += log(l) * w;
-    }
-  }
-  sh[threadIdx.x] = s;
-  shf[threadIdx.x] = f;
-  __syncthreads();
-  for (int off = blockDim.x / 2; off > 0; off >>= 1) {
-    if ((int)threadIdx.x < off) {
-      sh[threadIdx.x] += sh[threadIdx.x + off];
-      shf[threadIdx.x] |= shf[threadIdx.x + off];
-    }
-    __syncthreads();
-  }
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) loglik_term(L[j], comps[(q0 + j) * SE + D], s, f);
+  loglik_block_reduce(s, f, sh, shf);
   if (threadIdx.x == 0) {
     *sum_out = sh[0];
     *flag_out = shf[0];

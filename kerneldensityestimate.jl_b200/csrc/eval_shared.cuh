@@ -1,0 +1,53 @@
+// eval_shared.cuh -- device helpers shared by the evaluation kernels (eval.cu) and the fused
+// golden-section LOOCV kernel (lcv.cu).  Both must produce bit-identical likelihoods, so the pieces
+// that define the arithmetic live here once.
+#pragma once
+#include "common.cuh"
+
+namespace kdeb200 {
+
+// Rows whose fast-path total is below EV_TINY (density < 1e-275: the point is > 35 bandwidths away from
+// every component) are recomputed here with libdevice exp, sequentially in leaf order, so that
+// subnormal values and exact zeros (the likelihood's zero rule) match the reference.
+constexpr double EV_TINY = 1e-275;
+static __device__ __noinline__ double exact_row(const double *__restrict__ comps, int SE, int D, int64_t N,
+                                         const double *__restrict__ xq, const double *__restrict__ ich, int64_t self) {
+  double s = 0.0;
+  for (int64_t i = 0; i < N; ++i) {
+    if (i == self) continue;
+    const double *r = comps + i * SE;
+    double acc = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double df = __dadd_rn(xq[k], -r[k]);
+      acc = __fma_rn(__dmul_rn(df, df), ich[k], acc);
+    }
+    s = __fma_rn(exp(acc), r[D], s);
+  }
+  return s;
+}
+
+// one row of sum_j W_j log L_j with the reference's zero rule (src/DualTree01.jl:460-468):
+// L_j == 0 && W_j != 0 => flag (-Inf); L_j == 0 && W_j == 0 contributes log(1) * 0
+__device__ __forceinline__ void loglik_term(double l, double w, double &s, int &f) {
+  if (l == 0.0) {
+    if (w != 0.0) f = 1;
+  } else {
+    s = __fma_rn(log(l), w, s);
+  }
+}
+
+// fixed-order tree reduction over the CTA (blockDim.x a power of two <= 1024): result in sh[0], shf[0]
+__device__ __forceinline__ void loglik_block_reduce(double s, int f, double *sh, int *shf) {
+  sh[threadIdx.x] = s;
+  shf[threadIdx.x] = f;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      sh[threadIdx.x] += sh[threadIdx.x + off];
+      shf[threadIdx.x] |= shf[threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace kdeb200

@@ -190,3 +190,34 @@ def test_eval_only_handle_then_gibbs_upgrade():
     _lib.check(_lib.lib().kdeb200_tree_info(p._dev(), None, None, None, C.byref(nb_full)))
     assert nb_full.value > 2 * nb_eval.value
     assert np.array_equal(before, K.evaluateDualTree(p, q)) and H0 == K.entropy(p)
+
+
+@pytest.mark.parametrize("d,N", [(1, 2), (1, 3), (1, 100), (2, 100), (3, 257), (2, 512), (1, 513), (4, 700), (2, 3000)])
+def test_native_lcv_equals_stepwise_mirror(d, N):
+    """kdeb200_kde_lcv (fused single-launch golden section for N <= 512, host loop above) gives the bits of the
+    call-by-call mirror of kde!(points) (src/KDE01.jl:13-23) and the oracle's bandwidths to 1e-10."""
+    rng = np.random.default_rng(1000 * d + N)
+    pts = mixture(rng, d, N) if N > 3 else rng.normal(size=(d, N))
+    calls_native, calls_mirror = [], []
+    bw = K.lcv_bandwidths(pts, _count=calls_native)
+    p0 = K.kde(pts, [1.0])
+    ref = np.zeros(d)
+    for i in range(d):
+        ref[i] = K.getBW(K.ksize(K.marginal(p0, [i + 1]), _count=calls_mirror))[0, 0]
+    assert np.array_equal(bw, ref), (bw, ref)
+    assert calls_native == calls_mirror
+    o = OKDE.kde_lcv(pts)
+    assert relerr(bw ** 2, o.arrays()["bandwidthMin"][:d]) < 1e-10
+    assert np.array_equal(K.getBW(K.kde(pts))[:, 0], np.sqrt(bw ** 2))
+
+
+def test_native_lcv_degenerate_inputs():
+    """identical points: every LOO likelihood is +Inf-free but the bracket collapses to the 1e-6 floor; one point is
+    refused like the reference (minimum over an empty range)."""
+    pts = np.ones((2, 50))
+    a = K.lcv_bandwidths(pts)
+    p0 = K.kde(pts, [1.0])
+    b = np.array([K.getBW(K.ksize(K.marginal(p0, [i + 1])))[0, 0] for i in range(2)])
+    assert np.array_equal(a, b)
+    with pytest.raises(K.KDEError):
+        K.lcv_bandwidths(np.zeros((1, 1)))
