@@ -226,3 +226,43 @@ def test_many_batches_tiny_schedules(M, N, T, Np):
     rng = np.random.default_rng(M * 100 + N * 10 + T)
     pairs = [make(rng, 2, N, 0.5 * j, bw=np.array([0.5, 0.7])) for j in range(M)]
     compare([p[0] for p in pairs], [p[1] for p in pairs], Np, T, rng)
+
+
+def _mmd2_unbiased(X, Y, gamma):
+    """unbiased MMD^2 with an RBF kernel exp(-gamma |x-y|^2); X, Y are n x d"""
+    def gram(A, B):
+        d2 = (A * A).sum(1)[:, None] + (B * B).sum(1)[None, :] - 2.0 * A @ B.T
+        return np.exp(-gamma * np.maximum(d2, 0.0))
+    n, m = len(X), len(Y)
+    Kxx, Kyy, Kxy = gram(X, X), gram(Y, Y), gram(X, Y)
+    return ((Kxx.sum() - np.trace(Kxx)) / (n * (n - 1)) + (Kyy.sum() - np.trace(Kyy)) / (m * (m - 1))
+            - 2.0 * Kxy.mean())
+
+
+@pytest.mark.parametrize("d,M,N", [(1, 2, 150), (2, 3, 200), (3, 4, 128)])
+def test_free_running_rng_two_sample_ks_and_mmd(d, M, N):
+    """Mode (b) of BASELINE.json: with free-running RNG (device Philox vs numpy streams fed to the oracle) the
+    two product sample sets pass a two-sample Kolmogorov-Smirnov test per dimension and a kernel MMD permutation
+    test.  Independent streams, so the samples differ; only their law must agree."""
+    from scipy.stats import ks_2samp
+    rng = np.random.default_rng(4242 + d)
+    pairs = [make(rng, d, N, 0.25 * j) for j in range(M)]
+    kt, ot = [p[0] for p in pairs], [p[1] for p in pairs]
+    Np, T = 1500, 5
+    gp, _ = K.prodAppxMSGibbsS(None, kt, None, None, Niter=T, Np=Np, seed=99)
+    nU, nN = O.prod_sizes(ot, Np, T)
+    ep, _ = O.gibbs(ot, Np, T, rng.random(nU), rng.standard_normal(nN))
+    for k in range(d):
+        assert ks_2samp(gp[k], ep[k]).pvalue > 1e-3, "KS rejects equality of dimension %d" % k
+    X, Y = gp.T, ep.T
+    Z = np.vstack([X, Y])
+    med = np.median(((Z[:400, None, :] - Z[None, :400, :]) ** 2).sum(-1))
+    gamma = 1.0 / max(med, 1e-12)
+    stat = _mmd2_unbiased(X, Y, gamma)
+    null = []
+    for _ in range(100):
+        perm = rng.permutation(len(Z))
+        null.append(_mmd2_unbiased(Z[perm[:Np]], Z[perm[Np:]], gamma))
+    assert stat <= np.quantile(null, 0.99) + 3 * np.std(null), (stat, np.quantile(null, 0.99))
+    # and a shifted law IS detected by the same statistic (the test has power)
+    assert _mmd2_unbiased(X + 0.3 * X.std(0), Y, gamma) > np.quantile(null, 0.99) + 3 * np.std(null)
