@@ -35,7 +35,7 @@ struct Context {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  double *d_exptab = nullptr;  // 64-entry 2^(j/64) table
+  double *d_exptab = nullptr;  // KDE_EXP_TAB entries of 2^(j/TAB), high word biased (kde_exp_core)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
   int last_launches = 0;
@@ -115,7 +115,7 @@ inline ExpConsts make_exp_consts() { return ExpConsts{KDE_EXP_K, KDE_EXP_C1, 1.6
 // exp(x) = 2^(n / TAB) * e^r = 2^(n >> log2 TAB) * T[n mod TAB] * e^r,  n = rint(x*TAB/ln2), |r| <= ln2/(2 TAB).
 //   TAB = 2048 (16 KB shared memory): degree-3 Taylor (truncation r^4/24 <= 3.4e-17)  -> 7 FP64 instructions
 //   TAB = 256                       : degree-4 Taylor (r^5/120 <= 3.8e-17)            -> 8 FP64 instructions
-// (libdevice exp(): 17) + 5 integer/LDS instructions.  The reduction uses ONE constant: r = x - n*fl(ln2/TAB)
+// (libdevice exp(): 17) + 3 integer + 1 LDS instructions.  The reduction uses ONE constant: r = x - n*fl(ln2/TAB)
 // is exact up to its own rounding (FMA) and differs from the true remainder by n*(ln2/TAB - fl(.)), a relative
 // error of 3.4e-17*|x| in the result (< 1e-15 for every term that can matter in a sum, 2.4e-14 at the
 // clamp).  Valid for |x| <= 700 (normal results); anything else must be fixed up by the caller.  Branch-free
@@ -132,11 +132,12 @@ __device__ __forceinline__ double kde_exp_core(double x, const double *__restric
   const double q = __fma_rn(__fma_rn(r, 4.1666666666666664e-02, ec.sixth), r, 0.5);
 #endif
   const double p = __fma_rn(__dmul_rn(q, r), r, r);
-  const double T = tab[n & (KDE_EXP_TAB - 1)];
-  const double y = __fma_rn(T, p, T);
-  // exponent: mask first, then one shift-add (LEA): hi(y) + ((n >> log2 TAB) << 20)
-  const int nm = n & ~(KDE_EXP_TAB - 1);
-  return __hiloint2double(__double2hiint(y) + (nm << KDE_EXP_SHL), __double2loint(y));
+  // The table stores 2^(j/TAB) with (j << SHL) subtracted from its high word (context.cu), so ONE integer
+  // multiply-add, hi + n * 2^SHL, yields 2^(n >> log2 TAB) * 2^(j/TAB) without masking n: the j bits cancel.
+  // Scaling T before the FMA instead of y after it is exact (power of two, normal range) and off the critical path.
+  const double Tb = tab[n & (KDE_EXP_TAB - 1)];
+  const double T = __hiloint2double(__double2hiint(Tb) + n * (1 << KDE_EXP_SHL), __double2loint(Tb));
+  return __fma_rn(T, p, T);
 }
 
 // Clamped flavour: x < -700 is replaced by -700 with ONE integer instruction on the high word (negative NaN

@@ -59,7 +59,13 @@ static int init_device(int device) {
   KDE_CUDA(cudaEventCreate(&c.ev0));
   KDE_CUDA(cudaEventCreate(&c.ev1));
   double tab[KDE_EXP_TAB];
-  for (int j = 0; j < KDE_EXP_TAB; ++j) tab[j] = (double)exp2l((long double)j / (long double)KDE_EXP_TAB);
+  for (int j = 0; j < KDE_EXP_TAB; ++j) {  // 2^(j/TAB), high word biased by -(j << SHL): see kde_exp_core
+    const double v = (double)exp2l((long double)j / (long double)KDE_EXP_TAB);
+    uint64_t bits;
+    std::memcpy(&bits, &v, sizeof(bits));
+    bits -= (uint64_t)((uint32_t)j << KDE_EXP_SHL) << 32;
+    std::memcpy(&tab[j], &bits, sizeof(bits));
+  }
   KDE_CUDA(cudaMalloc(&c.d_exptab, sizeof(tab)));
   KDE_CUDA(cudaMemcpy(c.d_exptab, tab, sizeof(tab), cudaMemcpyHostToDevice));
   c.ready = true;
