@@ -281,12 +281,12 @@ def main():
             pass
         roof = {"bound": "fp64_fma_pipe", "achieved": ach * 2 / 1e12, "peak": dfma * 2 / 1e12, "unit": "TFLOP/s",
                 "frac": ach / dfma, "traffic": None,
-                "traffic_note": "ncu --set full on a 75,776-sample launch of the same kernel (profiles/r01_gibbs_v6_ncu.txt): "
-                                "dram read 0.26 GB + write 2.76 GB (local-memory checkpoints leaving L2), i.e. ~40 KB/sample "
+                "traffic_note": "ncu --set full on a 75,776-sample launch of the same kernel (profiles/r01_gibbs_v9_ncu.txt): "
+                                "dram read 0.19 GB + write 1.88 GB (local-memory checkpoints leaving L2), i.e. ~27 KB/sample "
                                 "or <0.5% of HBM bandwidth; a full 1M-sample launch does not finish under ncu replay",
                 "kernel": "gibbs_kernel<3,false>", "kernel_ms": k_ms,
                 # honest "issued" view next to the algorithmic one (SURVEY.md 8d asks for both): the kernel issues
-                # 13.1e6 FP64 instructions per sample (ncu, profiles/r01_gibbs_v8_ncu.txt) -- fewer than the model's
+                # 13.1e6 FP64 instructions per sample (ncu, profiles/r01_gibbs_v9_ncu.txt) -- fewer than the model's
                 # 17.9e6 slots because exp costs 7 instructions instead of 14 -- so frac can exceed 1
                 "issued_fp64_instr_per_sample": ISSUED_FP64_PER_SAMPLE,
                 "issued_frac": ISSUED_FP64_PER_SAMPLE * n_per / (k_ms * 1e-3) / dfma,
