@@ -28,9 +28,18 @@
 
 namespace kdeb200 {
 
-constexpr int GB_THREADS = 128;
-constexpr int GB_STAGES = 3;
-constexpr int GB_TILE_BYTES = 8192;
+#ifndef GB_THREADS_N
+#define GB_THREADS_N 128
+#endif
+#ifndef GB_STAGES_N
+#define GB_STAGES_N 3
+#endif
+#ifndef GB_TILE_N
+#define GB_TILE_N 8192
+#endif
+constexpr int GB_THREADS = GB_THREADS_N;  // chains per CTA
+constexpr int GB_STAGES = GB_STAGES_N;    // ring depth
+constexpr int GB_TILE_BYTES = GB_TILE_N;  // bytes per ring stage
 constexpr int GB_MAXCK = 64;  // checkpoints per draw
 #ifndef GB_UNROLL_A
 #define GB_UNROLL_A 4
