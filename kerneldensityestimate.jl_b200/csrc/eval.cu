@@ -5,7 +5,7 @@
 // FORCE_EVAL_DIRECT = true: evalDirect :130-162 over distGauss! :14-47 at leaf x leaf, then the
 // normalisation :325-341; evalAvgLogL :450-470 / entropy :505-508 for the fused likelihood.
 //
-// Mapping: one thread owns Q query points (registers), the CTA streams the component records
+// Mapping: one thread owns Q = ev_q(d) query points (registers), the CTA streams the component records
 // [x_0..x_{d-1}, w] (leaf order, the reference's summation order) through a 3-stage shared-memory
 // ring filled by 1-D TMA bulk copies; every lane reads the same record (broadcast LDS), so the
 // kernel is bound by the FP64 pipe (3d + 8 FP64 instructions per pair), not by memory.
@@ -212,9 +212,26 @@ __global__ void loglik_reduce_kernel(const double *L, const double *comps, int S
 }
 
 // ---------------------------------------------------------------- host side --------------
+// query points per thread: more rows per record load and per loop trip.  Swept on the B200 at 200k x 200k
+// (tools/bench_eval_dims.py): d = 1: 6 beats 2 by 8 % and 8 by 4 %; d = 2: 4; d = 3, 4: 2 (3 and 4 are 1-11 % slower);
+// d = 5, 6: 2 beats 1 by 2-10 %; d = 7, 8: 1.
+#ifndef EV_Q1
+#define EV_Q1 6
+#endif
+#ifndef EV_Q2
+#define EV_Q2 4
+#endif
+#ifndef EV_Q4
+#define EV_Q4 2
+#endif
+#ifndef EV_Q6
+#define EV_Q6 2
+#endif
+constexpr int ev_q(int d) { return d == 1 ? EV_Q1 : (d == 2 ? EV_Q2 : (d <= 4 ? EV_Q4 : (d <= 6 ? EV_Q6 : 1))); }
+
 template <int D, bool LOO>
 static cudaError_t launch_eval_d(const EvalParams &P, dim3 grid, size_t smem, cudaStream_t st) {
-  constexpr int Q = (D <= 4) ? 2 : 1;
+  constexpr int Q = ev_q(D);
   auto kern = eval_kernel<D, Q, LOO>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -239,7 +256,7 @@ static cudaError_t launch_eval(int d, const EvalParams &P, dim3 grid, size_t sme
   return cudaErrorInvalidValue;
 }
 
-static int queries_per_cta(int d) { return EV_THREADS * ((d <= 4) ? 2 : 1); }
+static int queries_per_cta(int d) { return EV_THREADS * ev_q(d); }
 
 // Evaluate rows.  loo: rows are bd's own leaves q0..q0+M-1 (d_pos ignored); d_out is written
 // through perm when `scatter`, else in row order.  bw_var overrides the tree's variances.
