@@ -16,7 +16,16 @@
 namespace kdeb200 {
 
 constexpr int F32_THREADS = 128;
-constexpr int F32_Q = 4;
+#ifndef F32_Q_N
+#define F32_Q_N 3
+#endif
+#ifndef F32_UNR
+#define F32_UNR 4
+#endif
+// swept on the B200 (tools/bench_f32.py, 500k x 500k): 3 queries per thread with 4 component pairs per loop trip
+// beats 4 x 2 by 14 % at d = 3; 6 or 8 queries per thread lose 10-20 %
+constexpr int F32_Q = F32_Q_N;  // query points per thread
+constexpr int F32_UNROLL = F32_UNR;
 constexpr int F32_STAGES = 3;
 constexpr int F32_TILE_BYTES = 8192;
 
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_cons
 #pragma unroll
     for (int i = 0; i < Q; ++i) part[i] = 0ull;
     if (!check) {
-#pragma unroll 2
+#pragma unroll F32_UNROLL
       for (int c = 0; c < cnt; ++c) {
         f32x2 r2[SP / 2];
 #pragma unroll
