@@ -62,9 +62,13 @@ __device__ __forceinline__ double quad(const double (&x)[D], const double (&r)[S
   return acc;
 }
 
+#ifndef EV_R
+#define EV_R 2
+#endif
 template <int D, int Q, bool LOO>
 __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant__ EvalParams P) {
   constexpr int SE = Rec<D>::SE;
+  constexpr int R = EV_R;  // component records per loop trip
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tiles = reinterpret_cast<double *>(smem_raw);
   __shared__ __align__(16) double tab[KDE_EXP_TAB];
@@ -122,23 +126,23 @@ __global__ void __launch_bounds__(EV_THREADS) eval_kernel(const __grid_constant_
     const double *rec = tiles + (size_t)(t % EV_STAGES) * (EV_TILE_BYTES / 8);
     const bool check = LOO && (a < qhi) && (a + cnt > qlo);
     if (!check) {
-      // branch-free exp for every pair, 2 records x Q queries per iteration (independent chains in one basic
+      // branch-free exp for every pair, R records x Q queries per iteration (independent chains in one basic
       // block).  Exponents below -700 are clamped (terms <= 1e-304); rows whose total ends up below
       // EV_TINY are recomputed exactly at the end, so this never shows in a result.
       int c = 0;
-      for (; c + 2 <= cnt; c += 2) {
-        double ra[SE], rb[SE], e[2][Q];
-        load_rec<SE>(rec + c * SE, ra);
-        load_rec<SE>(rec + (c + 1) * SE, rb);
+      for (; c + R <= cnt; c += R) {
+        double rr[R][SE], e[R][Q];
+#pragma unroll
+        for (int r = 0; r < R; ++r) load_rec<SE>(rec + (c + r) * SE, rr[r]);
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
-          e[0][i] = kde_exp_flush(quad<D>(x[i], ra, ich), tab, P.ec);
-          e[1][i] = kde_exp_flush(quad<D>(x[i], rb, ich), tab, P.ec);
+#pragma unroll
+          for (int r = 0; r < R; ++r) e[r][i] = kde_exp_flush(quad<D>(x[i], rr[r], ich), tab, P.ec);
         }
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
-          sum[i] = __fma_rn(e[0][i], ra[D], sum[i]);
-          sum[i] = __fma_rn(e[1][i], rb[D], sum[i]);
+#pragma unroll
+          for (int r = 0; r < R; ++r) sum[i] = __fma_rn(e[r][i], rr[r][D], sum[i]);  // component order
         }
       }
       for (; c < cnt; ++c) {
