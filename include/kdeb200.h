@@ -136,6 +136,16 @@ int kdeb200_loo_partial(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int
  * kernel.  Both give the bits of the call-by-call route through kdeb200_loo_entropy. */
 int kdeb200_kde_lcv(int d, int64_t N, const double *points, double *bw_std_out, int *nloo_calls_out);
 
+/* The same with the leaf rows [j0, j1) of every nLOO_LL evaluation owned by this process (one process
+ * per GPU): after each partial evaluation the library calls allreduce(&sum, &zero_flag, user), which
+ * must replace sum by its total over the processes and zero_flag by its maximum (MPI_Allreduce, an NCCL
+ * all-reduce on two scalars, ...) and return 0.  Every process runs the same golden-section loop on the
+ * same totals and gets the same bandwidths.  N <= 512 is computed redundantly by every process. */
+typedef int (*kdeb200_allreduce_fn)(double *sum, int *zero_flag, void *user);
+int kdeb200_kde_lcv_sharded(int d, int64_t N, const double *points, int64_t j0, int64_t j1,
+                            kdeb200_allreduce_fn allreduce, void *user, double *bw_std_out,
+                            int *nloo_calls_out);
+
 /* ---- measurement ----------------------------------------------------------------------------
  * Pipe-rate microbenchmarks for the roofline denominators: dependent-free DFMA,
  * FFMA and MUFU.EX2 loops over the whole chip.  which: 0 = DFMA, 1 = FFMA, 2 = MUFU.EX2.

@@ -127,6 +127,21 @@ function lcv_bandwidths(points::Matrix{Float64})
   return bw
 end
 
+# multi-GPU form (one Julia process per GPU): this process owns leaf rows j0+1:j1 of every nLOO_LL evaluation;
+# `allreduce` is a C-callable that sums the partial likelihood and maxes the zero flag over the processes, e.g.
+#   function ar(ps::Ptr{Float64}, pf::Ptr{Cint}, ::Ptr{Cvoid})::Cint
+#     unsafe_store!(ps, MPI.Allreduce(unsafe_load(ps), +, comm)); unsafe_store!(pf, MPI.Allreduce(unsafe_load(pf), max, comm)); 0
+#   end
+#   lcv_bandwidths_sharded(points, j0, j1, @cfunction(ar, Cint, (Ptr{Float64}, Ptr{Cint}, Ptr{Cvoid})))
+function lcv_bandwidths_sharded(points::Matrix{Float64}, j0::Integer, j1::Integer, allreduce::Ptr{Cvoid})
+  d, N = size(points)
+  bw = zeros(d)
+  GC.@preserve points bw check(ccall((:kdeb200_kde_lcv_sharded, LIB), Cint,
+    (Cint, Int64, Ptr{Float64}, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cint}),
+    d, N, points, j0, j1, allreduce, C_NULL, bw, C_NULL))
+  return bw
+end
+
 # nLOO_LL with the device tree reused across the ~20 golden-section steps of one ksize call
 function nLOO_LL(alpha::Float64, bd::BallTreeDensity, dt::DeviceTree)
   a2 = alpha^2

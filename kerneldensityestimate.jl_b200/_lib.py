@@ -14,6 +14,8 @@ u8p = C.POINTER(C.c_uint8)
 tree_t = C.c_void_p
 
 # name -> (restype, argtypes); kept in sync with include/kdeb200.h (tests/test_abi.py checks it)
+allreduce_fn = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p)
+
 SIGNATURES = {
     "kdeb200_last_error": (C.c_char_p, []),
     "kdeb200_version": (C.c_int, []),
@@ -39,6 +41,8 @@ SIGNATURES = {
     "kdeb200_loo_entropy": (C.c_int, [tree_t, f64p, f64p]),
     "kdeb200_loo_partial": (C.c_int, [tree_t, f64p, C.c_int64, C.c_int64, f64p, C.POINTER(C.c_int)]),
     "kdeb200_kde_lcv": (C.c_int, [C.c_int, C.c_int64, f64p, f64p, C.POINTER(C.c_int)]),
+    "kdeb200_kde_lcv_sharded": (C.c_int, [C.c_int, C.c_int64, f64p, C.c_int64, C.c_int64, allreduce_fn, C.c_void_p, f64p,
+                                          C.POINTER(C.c_int)]),
     "kdeb200_pipe_peak": (C.c_int, [C.c_int, C.c_int, f64p, f64p]),
     "kdeb200_dfma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, f64p]),
     "kdeb200_last_kernel_ms": (C.c_int, [f64p, C.POINTER(C.c_int)]),

@@ -480,16 +480,17 @@ def updateBandwidth(bd, bw):
     bd.bandwidthMax = bd.bandwidthMin = bd.bandwidth[N * d:].copy()
 
 
-def nLOO_LL(alpha, bd, addop=None, diffop=None):
-    """src/CrossValidation.jl:15-24 -- multiply, evaluate, divide back (ulp drift included)."""
+def nLOO_LL(alpha, bd, addop=None, diffop=None, _entropy=None):
+    """src/CrossValidation.jl:15-24 -- multiply, evaluate, divide back (ulp drift included).
+    _entropy replaces entropy(bd) (dist.kde_sharded: rows partitioned over the ranks)."""
     alpha = alpha * alpha
     updateBandwidth(bd, bd.bandwidth * alpha)
-    H = entropy(bd, addop, diffop)
+    H = entropy(bd, addop, diffop) if _entropy is None else _entropy(bd)
     updateBandwidth(bd, bd.bandwidth / alpha)
     return H
 
 
-def golden(bd, ax, bx, cx, tol, addop=None, diffop=None, _count=None):
+def golden(bd, ax, bx, cx, tol, addop=None, diffop=None, _count=None, _entropy=None):
     """Golden-section minimisation of nLOO_LL (src/CrossValidation.jl:44-98); host scalar loop."""
     Cc = (3.0 - math.sqrt(5.0)) / 2.0
     R = 1.0 - Cc
@@ -498,20 +499,20 @@ def golden(bd, ax, bx, cx, tol, addop=None, diffop=None, _count=None):
         x1, x2 = bx, bx + Cc * (cx - bx)
     else:
         x1, x2 = bx - Cc * (bx - ax), bx
-    f1 = nLOO_LL(x1, bd, addop, diffop)
-    f2 = nLOO_LL(x2, bd, addop, diffop)
+    f1 = nLOO_LL(x1, bd, addop, diffop, _entropy)
+    f2 = nLOO_LL(x2, bd, addop, diffop, _entropy)
     n = 2
     while abs(x3 - x0) > tol * (abs(x1) + abs(x2)):
         if f2 < f1:
             x0, x1 = x1, x2
             x2 = R * x1 + Cc * x3
             f1 = f2
-            f2 = nLOO_LL(x2, bd, addop, diffop)
+            f2 = nLOO_LL(x2, bd, addop, diffop, _entropy)
         else:
             x3, x2 = x2, x1
             x1 = R * x2 + Cc * x0
             f2 = f1
-            f1 = nLOO_LL(x1, bd, addop, diffop)
+            f1 = nLOO_LL(x1, bd, addop, diffop, _entropy)
         n += 1
     if _count is not None:
         _count.append(n)
@@ -528,12 +529,13 @@ def neighborMinMax(bd):
     return minm, maxm
 
 
-def ksize(bd, addop=None, diffop=None, _count=None):
+def ksize(bd, addop=None, diffop=None, _count=None, _entropy=None):
     """src/CrossValidation.jl:110-120"""
     _require_euclidean(addop=addop, diffop=diffop)
     minm, maxm = neighborMinMax(bd)
     p = kde(getPoints(bd), [(minm + maxm) / 2.0], getWeights(bd))
-    ks, _ = golden(p, 2.0 * minm / (minm + maxm), 1.0, 2.0 * maxm / (minm + maxm), 1e-2, _count=_count)
+    ks, _ = golden(p, 2.0 * minm / (minm + maxm), 1.0, 2.0 * maxm / (minm + maxm), 1e-2, _count=_count,
+                   _entropy=_entropy)
     ks = ks * (minm + maxm) / 2.0
     return kde(getPoints(p), [ks], getWeights(p))
 

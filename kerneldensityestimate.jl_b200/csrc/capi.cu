@@ -16,7 +16,8 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
                 const int64_t *left, const int64_t *right, const int64_t *perm, bool gibbs_records,
                 kdeb200_tree_t *out);
 int tree_destroy(kdeb200_tree_t t);
-int kde_lcv(int d, int64_t N, const double *points, double *bw_std_out, int *ncalls_out);
+int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb200_allreduce_fn allreduce, void *user,
+            double *bw_std_out, int *ncalls_out);
 int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int64_t q0, bool scatter,
                 const double *bw_var, double *d_out, cudaStream_t st, int *launches);
 int eval_device_f32(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, double *d_out, cudaStream_t st,
@@ -296,7 +297,14 @@ int kdeb200_loo_entropy(kdeb200_tree_t bd, const double *bw_var, double *H_out) 
 int kdeb200_kde_lcv(int d, int64_t N, const double *points, double *bw_std_out, int *nloo_calls_out) {
   KDE_SERIALISE();
   if (!points || !bw_std_out) KDE_FAIL(2, "kde_lcv: NULL argument");
-  return kde_lcv(d, N, points, bw_std_out, nloo_calls_out);
+  return kde_lcv(d, N, points, 0, N, nullptr, nullptr, bw_std_out, nloo_calls_out);
+}
+
+int kdeb200_kde_lcv_sharded(int d, int64_t N, const double *points, int64_t j0, int64_t j1,
+                            kdeb200_allreduce_fn allreduce, void *user, double *bw_std_out, int *nloo_calls_out) {
+  KDE_SERIALISE();
+  if (!points || !bw_std_out || !allreduce) KDE_FAIL(2, "kde_lcv_sharded: NULL argument");
+  return kde_lcv(d, N, points, j0, j1, allreduce, user, bw_std_out, nloo_calls_out);
 }
 
 int kdeb200_pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms) {

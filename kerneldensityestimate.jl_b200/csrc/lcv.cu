@@ -186,11 +186,20 @@ struct Golden {
 
 }  // namespace
 
-int kde_lcv(int d, int64_t N, const double *points, double *bw_std_out, int *ncalls_out) {
+// j0, j1 and allreduce: this process owns the leaf rows [j0, j1) of every nLOO_LL evaluation and the callback sums the
+// partial likelihood (and ORs the zero flag) over the processes -- the multi-GPU split of SURVEY.md 8e.  allreduce ==
+// nullptr: single process, all rows.  Small N runs the fused kernel redundantly on every process (no exchange needed).
+int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb200_allreduce_fn allreduce,
+            void *user, double *bw_std_out, int *ncalls_out) {
   if (int rc = ensure_init()) return rc;
   if (d < 1) KDE_FAIL(3, "kde_lcv: d must be >= 1");
   if (N < 2) KDE_FAIL(3, "kde_lcv: at least two points are needed for cross validation");
   if (2 * N >= (int64_t)std::numeric_limits<int32_t>::max()) KDE_FAIL(3, "kde_lcv: N too large");
+  if (!allreduce) {
+    j0 = 0;
+    j1 = N;
+  }
+  if (j0 < 0 || j1 > N || j0 > j1) KDE_FAIL(3, "kde_lcv: bad row range [%lld,%lld) of %lld", (long long)j0, (long long)j1, (long long)N);
   Context &c = ctx();
   const Golden G;
   const double tol = 1e-2;
@@ -283,12 +292,17 @@ int kde_lcv(int d, int64_t N, const double *points, double *bw_std_out, int *nca
     auto nloo = [&](double alpha, double &H) -> int {
       const double a2 = alpha * alpha;
       b = b * a2;
-      if (int r = loo_partial_device(t, &b, 0, N, d_sum, d_flag, c.stream, &launches)) return r;
-      double hs[9];
-      KDE_CUDA(cudaMemcpyAsync(hs, d_sum, sizeof(hs), cudaMemcpyDeviceToHost, c.stream));
-      KDE_CUDA(cudaStreamSynchronize(c.stream));
+      double hs[9] = {0};
+      if (j1 > j0) {
+        if (int r = loo_partial_device(t, &b, j0, j1, d_sum, d_flag, c.stream, &launches)) return r;
+        KDE_CUDA(cudaMemcpyAsync(hs, d_sum, sizeof(hs), cudaMemcpyDeviceToHost, c.stream));
+        KDE_CUDA(cudaStreamSynchronize(c.stream));
+      }
       int flag;
       std::memcpy(&flag, &hs[8], sizeof(int));
+      if (allreduce) {
+        if (int r = allreduce(&hs[0], &flag, user)) KDE_FAIL(9, "kde_lcv: the all-reduce callback failed (%d)", r);
+      }
       H = flag ? std::numeric_limits<double>::infinity() : -hs[0];
       b = b / a2;
       ++ncalls;

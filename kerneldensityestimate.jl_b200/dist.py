@@ -152,3 +152,50 @@ def loo_entropy_sharded(bd, bw_var=None, group=None, compute=None, device=None, 
         dist.all_reduce(tf, op=dist.ReduceOp.MAX, group=group)
         s, f = float(ts.item()), int(tf.item())
     return float("inf") if f else -s
+
+
+def kde_sharded(points, group=None, device=None, loo_factory=None):
+    """kde!(points) (src/KDE01.jl:3-27) with the leaf rows of every nLOO_LL evaluation block-partitioned over the
+    ranks: one all-reduce of (sum, zero flag) per golden-section step.  Every rank runs the same
+    golden loop on the same all-reduced likelihoods and returns the same density.  The loop is native
+    (kdeb200_kde_lcv_sharded, the exchange is a callback into torch.distributed); loo_factory(bd) -> compute(lo, hi)
+    replaces the CUDA worker and selects the step-by-step mirror instead (gloo tests)."""
+    import torch
+    pts = api._as_matrix(points)
+    d, N = pts.shape
+    rank, world = _world(group)
+    if loo_factory is None:
+        dist = _dist()
+        dev = _exchange_device(device, group) if world > 1 else None
+        failure = []
+
+        def exchange(psum, pflag, _user):
+            try:
+                if world > 1:
+                    ts = torch.tensor([psum[0]], dtype=torch.float64, device=dev)
+                    tf = torch.tensor([pflag[0]], dtype=torch.int32, device=dev)
+                    dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=group)
+                    dist.all_reduce(tf, op=dist.ReduceOp.MAX, group=group)
+                    psum[0], pflag[0] = float(ts.item()), int(tf.item())
+                return 0
+            except Exception as e:  # exceptions must not unwind through the C frames
+                failure.append(e)
+                return 1
+        cb = _lib.allreduce_fn(exchange)
+        a, b = shard_range(N, rank, world)
+        flat = np.ascontiguousarray(pts.T).ravel()
+        bw = np.zeros(d)
+        rc = _lib.lib().kdeb200_kde_lcv_sharded(d, N, _lib.fptr(flat), a, b, cb, None, _lib.fptr(bw), None)
+        if failure:
+            raise failure[0]
+        _lib.check(rc)
+        return api.kde(pts, bw)
+    p = api.kde(pts, [1.0])
+    bwds = np.zeros(d)
+
+    def ent(bd):
+        return loo_entropy_sharded(bd, bw_var=bd.bandwidthMin[:bd.bt.dims], group=group, device=device,
+                                   compute=loo_factory(bd))
+    for i in range(d):
+        bwds[i] = api.getBW(api.ksize(api.marginal(p, [i + 1]), _entropy=ent))[0, 0]
+    return api.kde(pts, bwds)

@@ -69,6 +69,22 @@ def _worker(rank, world, port, Np, out):
         assert abs(H - t.entropy()) < 1e-12 * abs(t.entropy())
         Hinf = kd.loo_entropy_sharded(BD(), compute=lambda a, b: (0.0, 1 if rank == 1 else 0), n_rows=N)
         assert Hinf == float("inf")
+
+        # kde!(points) with every nLOO_LL step's rows split over the ranks; numpy stands in for the CUDA worker
+        def loo_factory(bd):
+            n = bd.bt.num_points
+            x, w, var = bd.means[n:], bd.bt.weights[n:], float(bd.bandwidthMin[0])
+
+            def compute(lo, hi):
+                k = np.exp(-0.5 * (x[lo:hi, None] - x[None, :]) ** 2 / var) * w[None, :]
+                k[np.arange(hi - lo), np.arange(lo, hi)] = 0.0
+                Lj = k.sum(axis=1) / np.sqrt(2.0 * np.pi * var) / (1.0 - w[lo:hi])
+                return float(np.sum(np.log(Lj) * w[lo:hi])), int(np.any(Lj == 0.0))
+            return compute
+        lpts = np.concatenate([rng.standard_normal((2, 90)) * 0.5 - 1.0, rng.standard_normal((2, 60)) * 0.3 + 1.5], axis=1)
+        got = kd.kde_sharded(lpts, loo_factory=loo_factory)
+        ref = O.OKDE.kde_lcv(lpts).arrays()["bandwidthMin"][:2]
+        assert np.max(np.abs(got.bandwidthMin[:2] / ref - 1.0)) < 1e-9
         if rank == 0:
             out.put("ok")
     finally:

@@ -30,6 +30,9 @@ def _worker(rank, world, port, out):
         assert np.array_equal(kd.eval_sharded(trees[0], pos), K.evaluateDualTree(trees[0], pos))
         H = kd.loo_entropy_sharded(trees[1], trees[1].bandwidthMin[:3])
         assert abs(H - K.entropy(trees[1])) < 1e-12 * abs(H)
+        pts = np.concatenate([rng.standard_normal((2, 700)) * 0.5 - 1.0, rng.standard_normal((2, 500)) * 0.3 + 1.5], axis=1)
+        ks, k1 = kd.kde_sharded(pts), K.kde(pts)          # rows of every nLOO_LL step split over the two ranks
+        assert np.max(np.abs(K.getBW(ks)[:, 0] / K.getBW(k1)[:, 0] - 1.0)) < 1e-9
         if rank == 0:
             out.put("ok")
     finally:
