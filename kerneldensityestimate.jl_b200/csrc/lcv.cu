@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "eval_shared.cuh"
@@ -211,11 +212,24 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
     for (int64_t i = 0; i < N; ++i) ssum += w1[i];
     for (int64_t i = 0; i < N; ++i) w1[i] = w1[i] / ssum;
   }
-  std::vector<double> x(N);
+  // the d marginal trees are independent: one host thread each (the builder is a pure function of its arguments)
   std::vector<Marginal> margs(d);
-  for (int k = 0; k < d; ++k) {
-    for (int64_t i = 0; i < N; ++i) x[i] = points[i * d + k];
-    if (int rc = build_marginal(N, x.data(), w1, margs[k])) return rc;
+  {
+    std::vector<int> rcs(d, 0);
+    auto work = [&](int k) {
+      std::vector<double> x(N);
+      for (int64_t i = 0; i < N; ++i) x[i] = points[i * d + k];
+      rcs[k] = build_marginal(N, x.data(), w1, margs[k]);
+    };
+    if (d == 1 || N < 4096) {
+      for (int k = 0; k < d; ++k) work(k);
+    } else {
+      std::vector<std::thread> th;
+      for (int k = 0; k < d; ++k) th.emplace_back(work, k);
+      for (auto &t : th) t.join();
+    }
+    for (int k = 0; k < d; ++k)
+      if (rcs[k]) KDE_FAIL(rcs[k], "kde_lcv: building the marginal tree of dimension %d failed", k + 1);
   }
   auto finish = [&](int k, double xmin) {
     const Marginal &m = margs[k];
