@@ -266,3 +266,11 @@ def test_free_running_rng_two_sample_ks_and_mmd(d, M, N):
     assert stat <= np.quantile(null, 0.99) + 3 * np.std(null), (stat, np.quantile(null, 0.99))
     # and a shifted law IS detected by the same statistic (the test has power)
     assert _mmd2_unbiased(X + 0.3 * X.std(0), Y, gamma) > np.quantile(null, 0.99) + 3 * np.std(null)
+
+
+def test_very_large_trees_multi_tile_chunks():
+    """100 000-component trees: levels of up to 1e5 nodes (hundreds of tiles per draw, checkpoint chunks of 2048 nodes
+    spanning several tiles, pass 2 over long chunks) keep labels exact and points within 1e-10."""
+    rng = np.random.default_rng(31337)
+    pairs = [make(rng, 2, 100_000, 0.25 * j) for j in range(2)]
+    compare([p[0] for p in pairs], [p[1] for p in pairs], 130, 1, rng)
