@@ -221,3 +221,32 @@ def test_native_lcv_degenerate_inputs():
     assert np.array_equal(a, b)
     with pytest.raises(K.KDEError):
         K.lcv_bandwidths(np.zeros((1, 1)))
+
+
+def test_no_device_memory_growth_over_many_calls():
+    """200 rounds of create -> evaluate -> LOOCV -> product -> destroy leave the device's free memory where it was
+    (stream-ordered pool: blocks are reused, nothing leaks)."""
+    import ctypes as C
+    from kde_b200 import _lib
+
+    def free_bytes():
+        fb = C.c_size_t(0)
+        _lib.check(_lib.lib().kdeb200_device_props(None, None, None, None, C.byref(fb)))
+        return fb.value
+    rng = np.random.default_rng(5)
+
+    def round_trip():
+        p = K.kde(rng.normal(size=(2, 300)))
+        q = K.kde(rng.normal(size=(2, 200)) + 1.0, [0.4, 0.5])
+        K.evaluateDualTree(p, rng.normal(size=(2, 100)))
+        K.entropy(q)
+        K.prodAppxMSGibbsS(None, [p, q], None, None, Niter=2, Np=256, seed=1)
+        p._invalidate()
+        q._invalidate()
+    for _ in range(20):
+        round_trip()  # warm the pool
+    before = free_bytes()
+    for _ in range(200):
+        round_trip()
+    after = free_bytes()
+    assert before - after < 8 << 20, (before, after)
