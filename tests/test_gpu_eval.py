@@ -250,3 +250,38 @@ def test_no_device_memory_growth_over_many_calls():
         round_trip()
     after = free_bytes()
     assert before - after < 8 << 20, (before, after)
+
+
+def test_concurrent_host_threads_are_serialised():
+    """The reference is single-threaded; the library promises one call at a time per process.  Four host threads
+    hammering evaluation, LOOCV and Gibbs calls concurrently (ctypes drops the GIL) get the serial answers."""
+    import threading
+    rng = np.random.default_rng(12)
+    p = K.kde(mixture(rng, 3, 500), [0.3, 0.4, 0.5])
+    q = K.kde(mixture(rng, 3, 400) + 0.5, [0.4, 0.4, 0.4])
+    pos = rng.normal(size=(3, 300))
+    ref_e = K.evaluateDualTree(p, pos)
+    ref_h = K.entropy(q)
+    ref_g = K.prodAppxMSGibbsS(None, [p, q], None, None, Niter=3, Np=500, seed=3)
+    ref_b = K.lcv_bandwidths(pos)
+    p._dev(gibbs=True), q._dev(gibbs=True)  # handles are shared below; create them once
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(15):
+                assert np.array_equal(K.evaluateDualTree(p, pos), ref_e)
+                assert K.entropy(q) == ref_h
+                g = K.prodAppxMSGibbsS(None, [p, q], None, None, Niter=3, Np=500, seed=3)
+                assert np.array_equal(g[0], ref_g[0]) and np.array_equal(g[1], ref_g[1])
+                assert np.array_equal(K.lcv_bandwidths(pos), ref_b)
+                with pytest.raises(K.KDEError):  # the error channel is per thread
+                    K.evaluateDualTree(p, np.zeros((2, 3)))
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
