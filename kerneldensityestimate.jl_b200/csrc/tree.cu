@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "tree.cuh"
@@ -27,8 +28,6 @@ struct Builder {
   const double *pts;          // d x N, original order
   std::vector<int64_t> ord;   // leaf slot -> original index
   int64_t *left, *right, *lowest, *highest;
-  int64_t next = 2;
-  std::vector<int64_t> post;  // internal nodes in calcStats order
 
   inline double key(int64_t slot, int dim) const { return pts[ord[slot] * d + dim]; }
 
@@ -71,8 +70,12 @@ struct Builder {
     }
   }
 
-  // node ids are the reference's 1-based ids; slots are 0-based leaf positions (node = N+1+slot)
-  void topo(int64_t lo, int64_t hi, int64_t root) {
+  // node ids are the reference's 1-based ids; slots are 0-based leaf positions (node = N+1+slot).
+  // The reference hands out internal ids from a running counter in depth-first order (src/BallTree01.jl:415-434);
+  // a subtree over n >= 2 leaves consumes exactly n - 2 of them below its root, so the first free id of every
+  // subtree is known up front (next0) and disjoint subtrees can be built by different host threads.
+  // post: internal nodes in calcStats order (children before parents).
+  void topo(int64_t lo, int64_t hi, int64_t root, int64_t next0, std::vector<int64_t> &post, int par_depth) {
     const int64_t nlo = N + 1 + lo, nhi = N + 1 + hi;
     if (lo == hi) {  // single-point tree
       lowest[root - 1] = nlo;
@@ -85,15 +88,29 @@ struct Builder {
     const int dim = spread_dim(lo, hi);
     const int64_t split = (lo + hi) / 2;
     nth(dim, split, lo, hi);
-    int64_t l, r;
-    if (split <= lo) l = nlo; else l = next++;
-    if (split + 1 >= hi) r = nhi; else r = next++;
+    int64_t l, r, nxt = next0;
+    if (split <= lo) l = nlo; else l = nxt++;
+    if (split + 1 >= hi) r = nhi; else r = nxt++;
     lowest[root - 1] = nlo;
     highest[root - 1] = nhi;
     left[root - 1] = l;
     right[root - 1] = r;
-    if (l != nlo) topo(lo, split, l);
-    if (r != nhi) topo(split + 1, hi, r);
+    const int64_t nleft = split - lo + 1;
+    const int64_t next_right = nxt + (nleft >= 2 ? nleft - 2 : 0);
+    if (par_depth > 0 && hi - lo + 1 >= 32768 && l != nlo && r != nhi) {
+      std::vector<int64_t> post_left;
+      post_left.reserve((size_t)nleft);
+      std::thread th([&] { topo(lo, split, l, nxt, post_left, par_depth - 1); });
+      std::vector<int64_t> post_right;
+      post_right.reserve((size_t)(hi - split));
+      topo(split + 1, hi, r, next_right, post_right, par_depth - 1);
+      th.join();
+      post.insert(post.end(), post_left.begin(), post_left.end());
+      post.insert(post.end(), post_right.begin(), post_right.end());
+    } else {
+      if (l != nlo) topo(lo, split, l, nxt, post, 0);
+      if (r != nhi) topo(split + 1, hi, r, next_right, post, 0);
+    }
     post.push_back(root);
   }
 };
@@ -123,8 +140,11 @@ int tree_build_host(int d, int64_t N, const double *points, const double *weight
     lowest[i] = highest[i] = left[i] = i + 1;
     right[i] = -1;
   }
-  b.post.reserve(N);
-  b.topo(0, N - 1, 1);
+  std::vector<int64_t> post;
+  post.reserve(N);
+  int par_depth = 4;  // up to 16 host threads on large inputs; KDEB200_BUILD_PAR_DEPTH=0 builds on the calling thread
+  if (const char *e = getenv("KDEB200_BUILD_PAR_DEPTH")) par_depth = atoi(e);
+  b.topo(0, N - 1, 1, 2, post, par_depth);
 
   for (int64_t s = 0; s < N; ++s) {  // gather the leaf payload once
     const int64_t o = b.ord[s], node = N + s;
@@ -136,7 +156,7 @@ int tree_build_host(int d, int64_t N, const double *points, const double *weight
       bandwidth[node * d + k] = bw_var[k];
     }
   }
-  for (int64_t e : b.post) {  // node statistics, children before parents
+  for (int64_t e : post) {  // node statistics, children before parents
     const int64_t root = e < 0 ? -e : e;
     const int64_t L = left[root - 1];
     const int64_t R = e < 0 ? L : right[root - 1];  // N == 1: right temporarily aliases left

@@ -47,7 +47,8 @@ def test_error_channel_without_gpu(built):
         K.evaluateDualTree(p, np.zeros((2, 4)))
 
 
-@pytest.mark.parametrize("d,N", [(1, 1), (1, 2), (1, 4), (2, 3), (3, 100), (4, 257), (2, 1024), (8, 33)])
+@pytest.mark.parametrize("d,N", [(1, 1), (1, 2), (1, 4), (2, 3), (3, 100), (4, 257), (2, 1024), (8, 33),
+                                 (3, 70001), (1, 140000)])  # the last two take the multi-threaded path
 def test_host_tree_builder_equals_oracle(built, d, N):
     import kde_b200 as K
     from oracle.oracle import OKDE
