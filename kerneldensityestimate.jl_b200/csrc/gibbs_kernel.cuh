@@ -183,6 +183,43 @@ __device__ __forceinline__ void pre_C(const double *__restrict__ r, const Hoist<
     sc = rs;
     return;
   }
+  if (D == 1 && !MASK) {  // d = 1: 1/c = rsqrt(c)^2
+    const double c0 = __dadd_rn(rr[1], h.cadd[0]);
+    const double d0 = __dadd_rn(rr[0], -h.mu[0]);
+    const double rs = kde_rsqrt(c0);
+    const double quad = __dmul_rn(__dmul_rn(d0, d0), __dmul_rn(rs, rs));
+    arg = __fma_rn(quad, -0.5, rr[2]);
+    sc = rs;
+    return;
+  }
+  if (D == 2 && !MASK) {  // the same idea at d = 2: 1/c0 = c1 R, 1/c1 = c0 R
+    const double c0 = __dadd_rn(rr[2], h.cadd[0]), c1 = __dadd_rn(rr[3], h.cadd[1]);
+    const double d0 = __dadd_rn(rr[0], -h.mu[0]), d1 = __dadd_rn(rr[1], -h.mu[1]);
+    const double rs = kde_rsqrt(__dmul_rn(c0, c1));
+    const double Rv = __dmul_rn(rs, rs);
+    double quad = __dmul_rn(__dmul_rn(d0, d0), __dmul_rn(c1, Rv));
+    quad = __fma_rn(__dmul_rn(d1, d1), __dmul_rn(c0, Rv), quad);
+    arg = __fma_rn(quad, -0.5, rr[4]);
+    sc = rs;
+    return;
+  }
+  if (D == 4 && !MASK) {  // ... and at d = 4 with two pair products: 1/c0 = c1 (c2 c3 R), 1/c2 = c3 (c0 c1 R), ...
+    const double c0 = __dadd_rn(rr[4], h.cadd[0]), c1 = __dadd_rn(rr[5], h.cadd[1]);
+    const double c2 = __dadd_rn(rr[6], h.cadd[2]), c3 = __dadd_rn(rr[7], h.cadd[3]);
+    const double d0 = __dadd_rn(rr[0], -h.mu[0]), d1 = __dadd_rn(rr[1], -h.mu[1]);
+    const double d2 = __dadd_rn(rr[2], -h.mu[2]), d3 = __dadd_rn(rr[3], -h.mu[3]);
+    const double c01 = __dmul_rn(c0, c1), c23 = __dmul_rn(c2, c3);
+    const double rs = kde_rsqrt(__dmul_rn(c01, c23));
+    const double Rv = __dmul_rn(rs, rs);
+    const double t01 = __dmul_rn(c23, Rv), t23 = __dmul_rn(c01, Rv);
+    double quad = __dmul_rn(__dmul_rn(d0, d0), __dmul_rn(c1, t01));
+    quad = __fma_rn(__dmul_rn(d1, d1), __dmul_rn(c0, t01), quad);
+    quad = __fma_rn(__dmul_rn(d2, d2), __dmul_rn(c3, t23), quad);
+    quad = __fma_rn(__dmul_rn(d3, d3), __dmul_rn(c2, t23), quad);
+    arg = __fma_rn(quad, -0.5, rr[8]);
+    sc = rs;
+    return;
+  }
   double quad = 0.0;
   double prod = 1.0;
 #pragma unroll
