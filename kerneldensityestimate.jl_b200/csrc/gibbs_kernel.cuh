@@ -55,7 +55,10 @@ enum : int { VAR_A = 0, VAR_B = 1, VAR_C = 2 };
 
 // nodes per software-pipelined group / double group of pass 1 (host and device must agree: the host
 // never picks a checkpoint chunk smaller than one double group once a level has two of them)
-__host__ __device__ constexpr int gb_unr(int D, int var) { return (D <= 4) ? ((var == VAR_C) ? GB_UNROLL_C : GB_UNROLL_A) : (D <= 5 ? 2 : 1); }
+#ifndef GB_UNROLL_D6
+#define GB_UNROLL_D6 1
+#endif
+__host__ __device__ constexpr int gb_unr(int D, int var) { return (D <= 4) ? ((var == VAR_C) ? GB_UNROLL_C : GB_UNROLL_A) : (D <= 5 ? 2 : (D == 6 ? GB_UNROLL_D6 : 1)); }
 __host__ __device__ constexpr int gb_dg(int D, int var) { return 2 * gb_unr(D, var); }
 
 struct alignas(16) Draw {
