@@ -285,3 +285,28 @@ def test_concurrent_host_threads_are_serialised():
     for t in th:
         t.join()
     assert not errors, errors
+
+
+def test_sharded_lcv_entry_point_single_process_and_callback_errors():
+    """kdeb200_kde_lcv_sharded with one process owning all rows == kdeb200_kde_lcv (large-N host loop); a failing
+    all-reduce callback surfaces as an error instead of unwinding through the C frames."""
+    import ctypes as C
+    from kde_b200 import _lib, dist as kd
+    rng = np.random.default_rng(77)
+    pts = mixture(rng, 2, 1500)
+    assert np.array_equal(K.getBW(kd.kde_sharded(pts))[:, 0], K.getBW(K.kde(pts))[:, 0])
+    calls = []
+
+    def two_halves(ps, pf, _user):  # pretend a second process contributed nothing
+        calls.append(ps[0])
+        return 0
+    flat = np.ascontiguousarray(pts.T).ravel()
+    bw = np.zeros(2)
+    cb = _lib.allreduce_fn(two_halves)
+    _lib.check(_lib.lib().kdeb200_kde_lcv_sharded(2, 1500, _lib.fptr(flat), 0, 1500, cb, None, _lib.fptr(bw), None))
+    assert len(calls) >= 20 and np.array_equal(bw, K.lcv_bandwidths(pts))
+    bad = _lib.allreduce_fn(lambda ps, pf, u: 5)
+    rc = _lib.lib().kdeb200_kde_lcv_sharded(2, 1500, _lib.fptr(flat), 0, 1500, bad, None, _lib.fptr(bw), None)
+    assert rc == 9 and b"all-reduce callback failed" in _lib.lib().kdeb200_last_error()
+    rc = _lib.lib().kdeb200_kde_lcv_sharded(2, 1500, _lib.fptr(flat), 10, 5, cb, None, _lib.fptr(bw), None)
+    assert rc == 3
