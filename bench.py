@@ -163,8 +163,11 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
+    # stdout carries exactly ONE JSON line: NCCL writes its banner / logs to stdout by default (seen at 4 and 8
+    # GPUs even at WARN level), so send them to stderr whatever level the caller asked for
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
+        os.environ["NCCL_DEBUG"] = "WARN"
 
     import torch
     import torch.distributed as dist
