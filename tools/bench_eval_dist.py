@@ -14,6 +14,7 @@ n = int(sys.argv[sys.argv.index("--n") + 1]) if "--n" in sys.argv else 1_000_000
 prec = K.F32 if "--f32" in sys.argv else K.F64
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 os.environ.setdefault("NCCL_DEBUG", "WARN")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the JSON line
 torch.cuda.set_device(local)
 K.init(local)
 if world > 1:

@@ -10,6 +10,7 @@ from kde_b200 import dist as kd
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 os.environ.setdefault("NCCL_DEBUG", "WARN")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the JSON line
 torch.cuda.set_device(local)
 K.init(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
