@@ -295,7 +295,13 @@ def main():
                 "issued_frac": ISSUED_FP64_PER_SAMPLE * n_per / (k_ms * 1e-3) / dfma,
                 "algorithmic_fp64_slots_per_sample": ALG_SLOTS_PER_SAMPLE, "kernel_evals_per_sample": evals,
                 "peak_source": "DFMA microbenchmark (kdeb200_pipe_peak) measured in this run; nominal 64/clk/SM x 148 x 1.965 GHz = 37.2 TFLOP/s",
-                "note": "path is FP64-FMA-pipe bound, not HBM/tensor (SURVEY.md 8d); HBM peak of MEASURED_PEAKS.json = %s GB/s unused" % peaks_file.get("hbm_gbs")}
+                # the HBM view of the same launch, for the record: compulsory bytes = trees in + points and labels out
+                "hbm_view": {"algorithmic_bytes": tree_bytes + n_per * (DIM * 8 + NDENS * 8),
+                             "achieved_GBs": (tree_bytes + n_per * (DIM * 8 + NDENS * 8)) / (k_ms * 1e-3) / 1e9,
+                             "peak_GBs": peaks_file.get("hbm_gbs"),
+                             "frac": ((tree_bytes + n_per * (DIM * 8 + NDENS * 8)) / (k_ms * 1e-3) / 1e9 / peaks_file["hbm_gbs"])
+                             if peaks_file.get("hbm_gbs") else None},
+                "note": "path is FP64-FMA-pipe bound, not HBM/tensor (SURVEY.md 8d): the HBM view above is ~1e-5 of the measured copy bandwidth"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             from oracle import oracle as O
