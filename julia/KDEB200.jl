@@ -60,7 +60,7 @@ function gibbs1!(Ndens::Int, trees::Vector{BallTreeDensity}, Np::Int, Niter::Int
                  pts::Vector{Float64}, ind::Matrix{Int},
                  randU::Union{Nothing,Vector{Float64}}, randN::Union{Nothing,Vector{Float64}};
                  addop=(+,), diffop=(-,), getMu=(KDE.getEuclidMu,), getLambda=(KDE.getEuclidLambda,),
-                 addEntropy::Bool=true, ndims::Int=maximum(Ndim.(trees)),
+                 glbs=nothing, addEntropy::Bool=true, ndims::Int=maximum(Ndim.(trees)),
                  partialDimMask::AbstractVector{<:BitVector}=[trues(ndims) for i in 1:Ndens],
                  seed::UInt64=rand(UInt64))
   (euclidean(addop, diffop) && all(f -> f === KDE.getEuclidMu, getMu) &&
@@ -71,12 +71,33 @@ function gibbs1!(Ndens::Int, trees::Vector{BallTreeDensity}, Np::Int, Niter::Int
   mask = UInt8[partialDimMask[j][k] ? 0x01 : 0x00 for k in 1:ndims, j in 1:Ndens]  # [j*d + k], column-major
   uptr = randU === nothing ? Ptr{Float64}(C_NULL) : pointer(randU)
   nptr = randN === nothing ? Ptr{Float64}(C_NULL) : pointer(randN)
-  GC.@preserve dts hs mask randU randN pts ind begin
+  # glbs.recordChoosen (src/MSGibbs01.jl:29-31, examples/ExtractingLabels.jl): the library records
+  # permutation[ind[j]] of the last sampleIndex call of every level into an Int64 array [Nlevels, Ndens, Np]
+  # (C order [sample][density][level]); it is unpacked into glbs.labelsChoosen[sample][density][level] below.
+  record = glbs !== nothing && glbs.recordChoosen
+  nlev = Ref{Cint}(0)
+  GC.@preserve dts hs check(ccall((:kdeb200_gibbs_sizes, LIB), Cint,
+    (Ptr{Ptr{Cvoid}}, Cint, Cint, Ref{Cint}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+    hs, Ndens, Niter, nlev, C_NULL, C_NULL, C_NULL))
+  rec = record ? Array{Int64,3}(undef, Int(nlev[]), Ndens, Np) : Array{Int64,3}(undef, 0, 0, 0)
+  GC.@preserve dts hs mask randU randN pts ind rec begin
     check(ccall((:kdeb200_gibbs, LIB), Cint,
                 (Ptr{Ptr{Cvoid}}, Cint, Int64, Cint, Cint, Ptr{UInt8}, Ptr{Float64}, Int64, Ptr{Float64}, Int64,
                  UInt64, Int64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
                 hs, Ndens, Np, Niter, addEntropy, mask, uptr, randU === nothing ? 0 : length(randU),
-                nptr, randN === nothing ? 0 : length(randN), seed, 0, Np, pts, ind, C_NULL))
+                nptr, randN === nothing ? 0 : length(randN), seed, 0, Np, pts, ind,
+                record ? pointer(rec) : Ptr{Int64}(C_NULL)))
+  end
+  if record   # same nesting as the reference fills it at :109-112 (entries of levels never visited are absent)
+    for s in 1:Np
+      glbs.labelsChoosen[s] = Dict{Int,Dict{Int,Int}}()
+      for j in 1:Ndens
+        glbs.labelsChoosen[s][j] = Dict{Int,Int}()
+        for l in 1:Int(nlev[])
+          rec[l, j, s] >= 0 && (glbs.labelsChoosen[s][j][l] = rec[l, j, s])
+        end
+      end
+    end
   end
   nothing
 end

@@ -81,12 +81,17 @@ class BallTreeDensity:
         self.bandwidthMax = bandwidth[N * d:].copy()
         self._handle = None
         self._handle_gibbs = False
+        self._bw_dirty = False  # host bandwidth changed since the device records were built
 
     # -- device residency --------------------------------------------------------------
-    def _dev(self, gibbs=False):
+    def _dev(self, gibbs=False, stale_bw_ok=False):
         """Device handle; evaluation / LOOCV callers get the leaf-only hand-over
-        (kdeb200_tree_create_eval), the first Gibbs use upgrades it to the full level records."""
+        (kdeb200_tree_create_eval), the first Gibbs use upgrades it to the full level records.
+        A handle whose bandwidth records predate an updateBandwidth! is rebuilt, unless the caller
+        passes the current variances with the call itself (stale_bw_ok: entropy / nLOO_LL)."""
         if self._handle is not None and gibbs and not self._handle_gibbs:
+            self._invalidate()
+        if self._handle is not None and self._bw_dirty and not stale_bw_ok:
             self._invalidate()
         if self._handle is None:
             h = _lib.tree_t()
@@ -101,6 +106,7 @@ class BallTreeDensity:
                                                      iptr(bt.permutation), C.byref(h)))
             self._handle = h
             self._handle_gibbs = gibbs
+            self._bw_dirty = False
         return self._handle
 
     def _invalidate(self):
@@ -360,7 +366,7 @@ def entropy(bd, addop=None, diffop=None):
     d = bd.bt.dims
     bw = np.ascontiguousarray(bd.bandwidthMin[:d], dtype=np.float64)
     H = C.c_double(0.0)
-    check(lib().kdeb200_loo_entropy(bd._dev(), fptr(bw), C.byref(H)))
+    check(lib().kdeb200_loo_entropy(bd._dev(stale_bw_ok=True), fptr(bw), C.byref(H)))
     return H.value
 
 
@@ -471,13 +477,18 @@ def from_string(text):
 
 # ------------------------------------------------------------------------- LOOCV -------------
 def updateBandwidth(bd, bw):
-    """updateBandwidth! (src/CrossValidation.jl:5-12).  The device copy is NOT re-uploaded: the
-    leaf variances travel with each kdeb200_loo_entropy call instead."""
+    """updateBandwidth! (src/CrossValidation.jl:5-12).  The device records are marked stale: the next
+    evaluation / Gibbs call re-uploads the density with the new bandwidth (entropy / nLOO_LL instead
+    send the d leaf variances with each kdeb200_loo_entropy call and keep the resident points)."""
     if bd.multibandwidth != 0:
         raise KDEError("updateBandwidth! -- multibandwidth==0 ELSE not implemented yet")
     N, d = bd.bt.num_points, bd.bt.dims
+    bw = np.ascontiguousarray(bw, dtype=np.float64).ravel()
+    if bw.size != 2 * N * d:
+        raise KDEError("updateBandwidth!: expected the full 2*N*d bandwidth array")
     bd.bandwidth = bw
     bd.bandwidthMax = bd.bandwidthMin = bd.bandwidth[N * d:].copy()
+    bd._bw_dirty = True
 
 
 def nLOO_LL(alpha, bd, addop=None, diffop=None, _entropy=None):

@@ -49,11 +49,11 @@ static int init_device(int device) {
   c.device = device;
   c.sm_count = prop.multiProcessorCount;
   KDE_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-  {  // keep freed blocks in the stream-ordered pool (the default returns them to the driver at every sync,
-     // which made tree create / destroy cost tens of milliseconds)
+  {  // keep up to 1 GiB of freed blocks in the stream-ordered pool (the default returns everything to the driver
+     // at every sync, which made tree create / destroy cost tens of milliseconds)
     cudaMemPool_t pool;
     KDE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = UINT64_MAX;
+    uint64_t keep = 1ull << 30;  // bounded: multi-GB staging buffers (injected randU) go back to the driver
     KDE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   KDE_CUDA(cudaEventCreate(&c.ev0));

@@ -242,6 +242,12 @@ int eval_device_f32(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, 
     P.ctr[k] = cs[k] = bd->root_mean[k];
     P.scl[k] = cs[8 + k] = std::sqrt(0.5 * 1.4426950408889634 / v);  // exp(-q/2) = 2^(-q/2 * log2 e)
     norm *= std::sqrt(v);
+    // FP32 coordinates are centred on the density mean and scaled to bandwidth units: their rounding error grows
+    // with extent / sigma and breaks the 1e-5 contract beyond ~2000 (1.0e-5 at 2000, 2.8e-5 at 5000).  No silent
+    // loss of accuracy and no hidden FP64 fallback: refuse, the caller picks KDEB200_F64.
+    if (!(bd->extent[k] * P.scl[k] <= 1500.0))
+      KDE_FAIL(5, "eval (FP32): data extent / bandwidth = %.3g in dimension %d exceeds the range in which FP32 "
+                  "coordinates keep 1e-5 relative accuracy; use KDEB200_F64", bd->extent[k] * P.scl[k], k + 1);
   }
   if (!bd->d_leaf32) {  // one-time FP32 shadow of the leaf records (freed with the tree)
     double *d_cs = nullptr;

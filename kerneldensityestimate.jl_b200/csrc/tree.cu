@@ -302,6 +302,16 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
   }
   for (int k = 0; k < d; ++k)
     if (!(t->hvar[k] > 0.0) || !std::isfinite(t->hvar[k])) degen = true;
+  // Range contract of the fast arithmetic (kde_exp_flush needs exponents <= 700, the one-rsqrt normaliser needs
+  // prod_k c_k to stay normal at d = 8): every variance in [1e-30, 1e30], every mean within 1e100.  Anything
+  // outside is refused by the Gibbs entry points (code 8) instead of producing a wrong CDF.
+  auto var_ok = [](double b) { return b >= 1e-30 && b <= 1e30; };
+  for (int k = 0; k < d; ++k)
+    if (!var_ok(t->hvar[k])) degen = true;
+  if (gibbs_records)
+    for (int64_t i = 0; i + 1 < N && !degen; ++i)
+      for (int k = 0; k < d; ++k)
+        if (!var_ok(bandwidth[i * d + k]) || !(std::fabs(means[i * d + k]) <= 1e100)) degen = true;
   t->degenerate = degen;
 
   // leaf-order evaluation records and labels
@@ -309,7 +319,12 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
   std::vector<int64_t> pr(N), lab(gibbs_records ? lists.back().size() : 0);
   for (int64_t s = 0; s < N; ++s) {
     const int64_t node = N + s;
-    for (int k = 0; k < d; ++k) leaf[s * t->SE + k] = means[node * d + k];
+    for (int k = 0; k < d; ++k) {
+      const double x = means[node * d + k];
+      leaf[s * t->SE + k] = x;
+      const double dev = std::fabs(x - t->root_mean[k]);
+      if (dev > t->extent[k] || dev != dev) t->extent[k] = dev;
+    }
     leaf[s * t->SE + d] = weights[node];
     pr[s] = perm[node] - 1;
     if (pr[s] < 0 || pr[s] >= N) {

@@ -108,8 +108,11 @@ def prod_sharded_device(handles, ndens, dims, Np_total, Niter, seed, d_points, d
     _lib.check(_lib.lib().kdeb200_gibbs_device(handles, ndens, Np_total, Niter, 1, None, None, 0, None, 0, seed, s0,
                                                s1, d_points.data_ptr(), d_indices.data_ptr(), None, st))
     if world > 1:
-        dist.all_gather_into_tensor(g_points, d_points, group=group)
-        dist.all_gather_into_tensor(g_indices, d_indices, group=group)
+        if Np_total % world != 0:  # all_gather_into_tensor needs equal blocks; the host variant pads instead
+            raise api.KDEError("prod_sharded_device: Np_total (%d) must be a multiple of the world size (%d); "
+                               "use prod_sharded for ragged splits" % (Np_total, world))
+        dist.all_gather_into_tensor(g_points, d_points[: s1 - s0], group=group)
+        dist.all_gather_into_tensor(g_indices, d_indices[: s1 - s0], group=group)
 
 
 # ----------------------------------------------------------------------------- evaluation ----
@@ -141,7 +144,8 @@ def loo_entropy_sharded(bd, bw_var=None, group=None, compute=None, device=None, 
         def compute(lo, hi):
             s, f = C.c_double(0.0), C.c_int(0)
             bw = None if bw_var is None else np.ascontiguousarray(bw_var, dtype=np.float64)
-            _lib.check(_lib.lib().kdeb200_loo_partial(bd._dev(), _lib.fptr(bw), lo, hi, C.byref(s), C.byref(f)))
+            _lib.check(_lib.lib().kdeb200_loo_partial(bd._dev(stale_bw_ok=bw is not None), _lib.fptr(bw), lo, hi,
+                                                      C.byref(s), C.byref(f)))
             return s.value, f.value
     s, f = compute(a, b)
     if world > 1:

@@ -376,6 +376,28 @@ int okde_evaluate(const okde *bd, const okde *loc, double *p) {
   return 0;
 }
 
+/* Rows [j0, j1) (0-based leaf positions, leaf order) of evaluate(bd, bd, ...) -- the same evalDirect sums as
+ * okde_evaluate, restricted to a block of query leaves so that full-size configurations (1e5 x 1e5) can be
+ * spot-checked in seconds.  out[j - j0] is the LOO density of leaf N+1+j; rows are independent (OpenMP). */
+int okde_loo_rows(const okde *bd, int64_t j0, int64_t j1, double *out, int nthreads) {
+  if (j0 < 0 || j1 > bd->num_points || j0 > j1) return 1;
+  const double norm = eval_norm(bd);
+  const int64_t first = bd->lowest_leaf[0];
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+  (void)nthreads;
+#endif
+#pragma omp parallel for schedule(static)
+  for (int64_t r = j0; r < j1; ++r) {
+    const int64_t j = first + r;
+    double pMin = 0.0, pMax = 0.0;
+    eval_direct_row(bd, bd, j, 1, &pMin, &pMax);
+    out[r - j0] = 0.5 * (pMin + pMax) / norm / (1.0 - WGT(bd, j));
+  }
+  return 0;
+}
+
 /* evaluateDualTree(bd, pos::Matrix) (src/DualTree01.jl:370-390).  The reference builds a
  * throw-away tree over pos (bw 1, weights 1/M) whose only effect under brute force is the
  * order in which rows are visited; each row's sum runs over bd's leaves in leaf order, so
@@ -615,6 +637,46 @@ static void calc_indices(gbglb *g) {
   for (int64_t j = 1; j <= g->Ndens; ++j) update_particles_variance(g, j);
 }
 
+/* getEuclidLambda = sum(lambdas) (src/MSGibbs01.jl:141).  Julia's Base.sum over a Vector{Float64} is a plain
+ * left-to-right loop for length < 16; from length 16 on it is `v = a[1] + a[2]; @simd for i in 3:n v += a[i]`
+ * (Base.mapreduce_impl, block 1024), which LLVM may vectorise with reassociation: VF lanes x IC interleaved
+ * accumulators consume VF*IC elements per trip while at least that many remain, the accumulators are folded
+ * (interleave copies left to right, then a log2 shuffle tree inside the vector) and the tail is added
+ * sequentially.  Whether the vector body runs at all for the 14 remaining elements of n = 16 depends on the
+ * host ISA (VF*IC = 16 on AVX2 and 32 on AVX-512 => scalar, i.e. sequential; 8 on SSE2 => one vector trip).
+ * okde_set_sum_simd(vf, ic) selects the emulated shape; (0, 0) = sequential (default, and what n < 16 always is).
+ * KDEB200_MAX_DENS == 16, so M = 16 is the only reachable length on that edge (tests/test_oracle_stats.py). */
+static int g_sum_vf = 0, g_sum_ic = 0;
+void okde_set_sum_simd(int vf, int ic) {
+  g_sum_vf = vf;
+  g_sum_ic = ic;
+}
+static double julia_sum(const double *a, int64_t n) {
+  if (n < 16 || g_sum_vf <= 0 || g_sum_ic <= 0 || g_sum_vf * g_sum_ic > 64) {
+    double s = 0.0;
+    for (int64_t j = 0; j < n; ++j) s += a[j];
+    return s;
+  }
+  const int vf = g_sum_vf, ic = g_sum_ic, W = vf * ic;
+  double acc[64];
+  for (int l = 0; l < W; ++l) acc[l] = 0.0;
+  acc[0] = a[0] + a[1]; /* the scalar start value enters lane 0 of the first accumulator */
+  int64_t i = 2;
+  for (; i + W <= n; i += W)
+    for (int l = 0; l < W; ++l) acc[l] += a[i + l];
+  double v[64];
+  for (int l = 0; l < vf; ++l) { /* fold the interleaved copies: ((v0 + v1) + v2) + ... */
+    double t = acc[l];
+    for (int c = 1; c < ic; ++c) t = acc[c * vf + l] + t;
+    v[l] = t;
+  }
+  for (int h = vf / 2; h >= 1; h /= 2) /* shuffle tree: upper half onto lower half */
+    for (int l = 0; l < h; ++l) v[l] = v[l] + v[l + h];
+  double s = v[0];
+  for (; i < n; ++i) s += a[i];
+  return s;
+}
+
 /* gaussianProductMeanCov! with getEuclidLambda / getEuclidMu
  * (src/MSGibbs01.jl:176-216, :141, :152-161) */
 static void gaussian_product_mean_cov(gbglb *g, int64_t dim, double *destMu, double *destCov, int64_t skip) {
@@ -633,9 +695,7 @@ static void gaussian_product_mean_cov(gbglb *g, int64_t dim, double *destMu, dou
       g->calcmu[j - 1] = 0.0;
     }
   }
-  double lam = 0.0;
-  for (int64_t j = 0; j < g->Ndens; ++j) lam += g->calclambdas[j]; /* sum(lambdas) */
-  *destCov = lam;
+  *destCov = julia_sum(g->calclambdas, g->Ndens); /* sum(lambdas) */
   *destCov = 1.0 / *destCov;
   double lambdamu = 0.0;
   for (int64_t z = 0; z < g->Ndens; ++z) lambdamu += g->calcmu[z] * g->calclambdas[z];

@@ -81,6 +81,10 @@ int okde_gibbs_omp(int64_t ndens, const okde *const *trees, int64_t Np, int64_t 
                    int nthreads);
 int okde_eval_points_omp(const okde *bd, int64_t M, const double *pos, double *p, int nthreads);
 int okde_max_threads(void);
+/* LOO densities of the leaf rows [j0, j1) (leaf order) of evaluate(bd, bd): full-size spot checks */
+int okde_loo_rows(const okde *bd, int64_t j0, int64_t j1, double *out, int nthreads);
+/* emulate Julia's @simd sum(lambdas) for Ndens >= 16 with vf lanes x ic interleaved accumulators; (0,0) = sequential */
+void okde_set_sum_simd(int vf, int ic);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,8 @@ def lib():
         L.okde_gibbs_omp.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_int64, C.c_int64, f64p, i64p, f64p,
                                      C.c_int64, f64p, C.c_int64, C.c_int, u8p, C.c_int]
         L.okde_max_threads.restype = C.c_int
+        L.okde_loo_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, f64p, C.c_int]
+        L.okde_set_sum_simd.argtypes = [C.c_int, C.c_int]
         _LIB = L
     return _LIB
 
@@ -188,6 +190,13 @@ class OKDE:
             lib().okde_eval_points(self.ptr, p.shape[1], _f(p), _f(out))
         return out
 
+    def loo_rows(self, j0, j1, nthreads=0):
+        """LOO densities of the leaf rows [j0, j1) in LEAF order (evaluate(bd, bd) restricted to a block)."""
+        out = np.zeros(j1 - j0)
+        if lib().okde_loo_rows(self.ptr, j0, j1, _f(out), int(nthreads)):
+            raise RuntimeError("loo_rows: bad row range")
+        return out
+
     def eval_avg_logl(self, other):
         return lib().okde_eval_avg_logl(self.ptr, other.ptr)
 
@@ -254,6 +263,11 @@ def prod_sizes(trees, Np, Niter):
     maxNp = max([Np] + [t.npts for t in trees])
     nlev = int(math.floor(math.log(float(maxNp)) / math.log(2.0) + 1.0))
     return Np * M * (Niter + 2) * nlev, d * Np * (nlev + 1)
+
+
+def set_sum_simd(vf=0, ic=0):
+    """Emulated shape of Julia's @simd sum(lambdas) for Ndens >= 16 (0, 0 = sequential)."""
+    lib().okde_set_sum_simd(int(vf), int(ic))
 
 
 def max_threads():

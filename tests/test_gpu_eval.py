@@ -310,3 +310,95 @@ def test_sharded_lcv_entry_point_single_process_and_callback_errors():
     assert rc == 9 and b"all-reduce callback failed" in _lib.lib().kdeb200_last_error()
     rc = _lib.lib().kdeb200_kde_lcv_sharded(2, 1500, _lib.fptr(flat), 10, 5, cb, None, _lib.fptr(bw), None)
     assert rc == 3
+
+
+def test_update_bandwidth_invalidates_the_device_records():
+    """updateBandwidth! (src/CrossValidation.jl:5-12) followed by evaluation / LOO / a product uses the NEW
+    bandwidth, like the reference: the cached device handle is rebuilt."""
+    rng = np.random.default_rng(41)
+    pts = mixture(rng, 2, 300)
+    p = K.kde(pts, [0.3, 0.4])
+    pos = rng.normal(size=(2, 64))
+    before = K.evaluateDualTree(p, pos)
+    K.updateBandwidth(p, p.bandwidth * 2.25)              # std x 1.5 on every node
+    fresh = K.kde(pts, [0.45, 0.6])
+    after = K.evaluateDualTree(p, pos)
+    assert relerr(after, K.evaluateDualTree(fresh, pos)) < 1e-13 and relerr(after, before) > 1e-3
+    assert relerr(K.evaluateDualTree(p, p), K.evaluateDualTree(fresh, fresh)) < 1e-13
+    assert relerr(p(pos), K.evaluateDualTree(fresh, pos)) < 1e-13
+    assert abs(K.entropy(p) - K.entropy(fresh)) < 1e-13 * abs(K.entropy(fresh))
+    g1 = K.prodAppxMSGibbsS(None, [p, p], None, None, Niter=2, Np=128, seed=9)
+    g2 = K.prodAppxMSGibbsS(None, [fresh, fresh], None, None, Niter=2, Np=128, seed=9)
+    assert np.array_equal(g1[1], g2[1]) and np.max(np.abs(g1[0] - g2[0])) < 1e-12
+    # nLOO_LL's multiply / divide-back leaves the (ulp-drifted) bandwidth in place and later calls see it
+    H = K.nLOO_LL(1.3, p)
+    o = OKDE.kde_bw(pts, [0.45, 0.6])
+    assert abs(H - o.nloo_ll(1.3)) <= 1e-12 * abs(H)
+    assert relerr(K.evaluateDualTree(p, pos), o.evaluate(pos)) < TOL   # the oracle drifted the same way
+    with pytest.raises(K.KDEError):
+        K.updateBandwidth(p, p.bandwidth[:10])
+
+
+def test_fp32_refuses_data_too_wide_for_its_contract():
+    """FP32 coordinates are centred and scaled to bandwidth units; beyond extent/sigma ~ 2000 their rounding breaks
+    the 1e-5 contract, so the library refuses (no silent accuracy loss, no hidden FP64 fallback)."""
+    rng = np.random.default_rng(2)
+    pts = np.hstack([rng.normal(size=(1, 200)), 5000.0 + rng.normal(size=(1, 200))])
+    p = K.kde(pts, [0.5])
+    x = pts[:, ::7]
+    assert relerr(K.evaluateDualTree(p, x), OKDE.kde_bw(pts, [0.5]).evaluate(x)) < TOL
+    with pytest.raises(K.KDEError, match="FP32"):
+        K.evaluateDualTree(p, x, precision=K.F32)
+    q = K.kde(pts, [5.0])                                  # the same data at a 10x wider bandwidth is fine
+    assert relerr(K.evaluateDualTree(q, x, precision=K.F32), K.evaluateDualTree(q, x)) < 1e-5
+
+
+def test_full_size_c3_loo_rows_and_kde():
+    """BASELINE config 3 at full size (kde! LOOCV of 100 000 x 4-D mixture points).
+    (a) One marginal's LOO sum at 100k rows -- component splits S > 1, eval_finalize_kernel and the 100k-row
+        likelihood reduction, which no smaller test reaches -- against the oracle's literal evalDirect rows
+        (okde_loo_rows) on 512 rows spread over the leaf range: 1e-12, through the full LOO evaluation and
+        through kdeb200_loo_partial(j0, j1).
+    (b) The whole kde!(points): the native loop equals the step-by-step mirror bit for bit on one dimension,
+        and the selected bandwidth beats its x2 / x0.5 neighbours on the oracle's row-subsampled likelihood."""
+    import ctypes as C
+    from kde_b200 import _lib
+    rng = np.random.default_rng(20261017)
+    N = 100_000
+    pts = mixture(rng, 4, N)
+    # (a) marginal of dimension 1 at a mid-bracket bandwidth
+    x = pts[:1]
+    h = 0.05
+    p, o = K.kde(x, [h]), OKDE.kde_bw(x, [h])
+    L = K.evaluateDualTree(p, p)                            # original order
+    perm = p.bt.permutation[N:] - 1                         # leaf -> original index
+    blocks = [(0, 128), (33_333, 33_333 + 128), (77_777, 77_777 + 128), (N - 128, N)]
+    s_tot = 0.0
+    for a, b in blocks:
+        exp = o.loo_rows(a, b, nthreads=8)
+        assert relerr(L[perm[a:b]], exp) < TOL
+        s, f = C.c_double(0), C.c_int(0)
+        bw = np.array([h * h])
+        _lib.check(_lib.lib().kdeb200_loo_partial(p._dev(), _lib.fptr(bw), a, b, C.byref(s), C.byref(f)))
+        w = p.bt.weights[N + a:N + b]
+        ref = float(np.sum(np.log(exp) * w))
+        assert f.value == 0 and abs(s.value - ref) <= 1e-12 * abs(ref)
+        s_tot += s.value
+    H = K.entropy(p)
+    w_all = p.bt.weights[N:]
+    assert abs(H + float(np.sum(np.log(L[perm]) * w_all))) <= 1e-11 * abs(H)   # reduction == sum of its rows
+    # (b) the full kde!(points): native loop == step-by-step mirror (dimension 1), and sane, positive bandwidths
+    calls = []
+    bw = K.lcv_bandwidths(pts, _count=calls)
+    assert bw.shape == (4,) and np.all(bw > 0.005) and np.all(bw < 0.5) and all(10 <= c <= 40 for c in calls)
+    cnt = []
+    pp = K.ksize(K.marginal(K.kde(pts, [1.0]), [1]), _count=cnt)
+    assert K.getBW(pp)[0, 0] == bw[0] and cnt[0] == calls[0]
+    # the selected bandwidth minimises the oracle's LOO likelihood on a fixed 2048-row subsample no worse than its
+    # +-10 % neighbours by more than the subsample noise (loose: this is a sanity bound, the bit-for-bit check is above)
+    rows = (0, 2048)
+    def sub_nll(hh):
+        oo = OKDE.kde_bw(x, [hh])
+        return -float(np.mean(np.log(oo.loo_rows(rows[0], rows[1], nthreads=8))))
+    c = sub_nll(bw[0])
+    assert c <= sub_nll(bw[0] * 2.0) and c <= sub_nll(bw[0] * 0.5)
