@@ -1,23 +1,38 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 hot path (contract: see the task statement).
 
-Workload (BASELINE.json configs[3], the one `metric` is quoted on; it fits one GPU):
-    prodAppxMSGibbsS of 8 densities x 4096 components, 3-D, Niter=5, 1,000,000 product samples
+Main workload (BASELINE.json configs[3], the one `metric` is quoted on; it fits one GPU):
+    C4: prodAppxMSGibbsS of 8 densities x 4096 components, 3-D, Niter=5, 1,000,000 product samples
     per GPU per step, free-running Philox streams, synthetic Gaussian-mixture data.
 A "step" is one such call.  `value` = product samples/s with the trees resident in HBM
 (kdeb200_gibbs_device on torch's current stream, CUDA events, L2 flushed between steps);
 `e2e` = the same through the host API (prodAppxMSGibbsS mirror -> kdeb200_gibbs): tree
 flatten + H2D and the D2H of points and labels inside the timed region.
-N > 1 (torchrun, one rank per GPU): every rank draws its own 1M-sample slice of an N x 1M-sample
-run (chains are addressed by global sample index, so results do not depend on N) and the slices
-are assembled with an NCCL all-gather inside the timed step -> "scaling": "weak".
 
-`--impl reference` times the CPU arm: the literal C restatement of the reference (oracle/,
-kind "port"; the reference itself is Julia and there is no julia binary on the box) with all
-host threads over independent chains, on a bounded sample of the same workload.
+N > 1 (torchrun, one rank per GPU): chains are addressed by global sample index, so results do not
+depend on N.  Two curves are measured in the same run:
+  weak   (the headline line, "scaling": "weak"): every rank draws its own 1M-sample slice of an N x 1M-sample run
+  strong ("strong" sub-record; BASELINE.json configs[3] "1M samples at 1/2/4/8 GPUs"): 1M samples in total,
+         1M / N per rank
+both with the NCCL all-gather of points + labels inside the timed step, and after the timed loops every rank
+recomputes a 4096-sample slice that a FOREIGN rank produced and compares it bit for bit with what the all-gather
+delivered ("gather_checked").
+
+`secondary` carries the other BASELINE configurations measured in the same run, each with its own roofline
+(algorithmic and issued) and cpu_baseline: C5 (1M x 1M brute-force evaluation, FP64 and FP32) and C3 (kde! LOOCV of
+100k x 4-D points: one nLOO_LL launch and the whole bandwidth search); at N > 1 their sharded forms.
+
+Issued-instruction and DRAM-traffic figures come from profiles/ncu_issued.json (tools/ncu_issued.py: ncu counters
+keyed by a hash of the kernel sources); if the sources changed since the capture they are reported as stale (null),
+never silently reused.
+
+`--impl reference` times the CPU arm: the literal C restatement of the reference (oracle/, kind "port"; the
+reference itself is Julia and there is no julia binary on the box) with all host threads over independent
+chains, on a bounded sample of the same workload.
 """
 import argparse
 import ctypes as C
+import importlib.util
 import json
 import os
 import statistics
@@ -34,10 +49,11 @@ sys.path.insert(0, ROOT)
 SEED = 20261017
 NDENS, NCOMP, DIM, NITER = 8, 4096, 3, 5
 SAMPLES_PER_GPU = 1_000_000
+GATHER_CHECK = 4096
 # algorithmic FP64-pipe slots per sample for this shape: 393216 leaf-level
 # evaluations x 22 + 196512 internal-level evaluations x 47
 ALG_SLOTS_PER_SAMPLE = 393216 * 22 + 196512 * 47
-ISSUED_FP64_PER_SAMPLE = 31035518826 * 32 / 75776  # executed DFMA+DMUL+DADD warp-instructions x 32 lanes / samples (ncu)
+ALG_SLOTS_EVAL = {1: 17, 3: 21}  # 2d + 1 + 14
 
 
 def synth_points(j):
@@ -50,6 +66,13 @@ def synth_points(j):
     return pts
 
 
+def mixture(rng, d, N, sigma=0.6):
+    """K=4 isotropic Gaussians on the first 4 corners of {+-2}^d (the C3 / C5 inputs; same law as tests/util.py)."""
+    corners = np.array([[(-2.0 if (c >> (d - 1 - k)) & 1 == 0 else 2.0) for k in range(d)] for c in range(min(4, 2 ** d))])
+    comp = rng.integers(0, len(corners), size=N)
+    return corners[comp].T + sigma * rng.standard_normal((d, N))
+
+
 def silverman(pts):
     d, N = pts.shape
     return pts.std(axis=1, ddof=1) * (4.0 / ((d + 2.0) * N)) ** (1.0 / (d + 4.0))
@@ -60,6 +83,28 @@ def host_cores():
         return max(1, len(os.sched_getaffinity(0)))
     except Exception:
         return os.cpu_count() or 1
+
+
+def _build_module():
+    spec = importlib.util.spec_from_file_location("kdeb200_build", os.path.join(ROOT, "kerneldensityestimate.jl_b200", "build.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def issued_record(label, err=sys.stderr):
+    """Entry `label` of profiles/ncu_issued.json if it was captured on the current kernel sources, else None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_issued.json")))[label]
+    except Exception as e:  # noqa: BLE001
+        print("[bench] no ncu record for %s (%s): issued/traffic figures are null" % (label, e), file=err)
+        return None
+    cur = _build_module().kernel_source_hash(rec["kind"])
+    if cur != rec["source_hash"]:
+        print("[bench] STALE ncu record for %s: kernel sources %s != profiled %s -- re-run tools/ncu_issued.py; "
+              "issued/traffic figures are null" % (label, cur, rec["source_hash"]), file=err)
+        return None
+    return rec
 
 
 class ClockSampler:
@@ -129,21 +174,156 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "product samples/sec (Gibbs, Niter=5)", "value": val, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(),
+        "config": workload_config(world),
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def workload_config():
+def workload_config(world=1):
     return {"workload": "C4: prodAppxMSGibbsS, 8 densities x 4096 components, 3-D, Niter=5, 1M samples per GPU per step",
             "ndens": NDENS, "components": NCOMP, "dims": DIM, "niter": NITER, "samples_per_gpu": SAMPLES_PER_GPU,
             "rng": "Philox4x32-10 (seed %d), free-running" % SEED,
             "bandwidth": "Silverman", "l2": "flushed between timed steps (256 MiB write); trees (5.3 MB) are L2-resident by design",
-            "multi_gpu": "weak: rank r draws samples [r*1M,(r+1)*1M) of one N*1M-sample run, NCCL all-gather of points+labels in the timed step"}
+            "multi_gpu": "weak (headline): rank r draws samples [r*1M,(r+1)*1M) of one N*1M-sample run; strong (sub-record "
+                         "'strong', BASELINE configs[3]): 1M samples in total, 1M/N per rank; both with the NCCL all-gather of "
+                         "points+labels in the timed step and a bit-exact check of a foreign rank's gathered slice afterwards",
+            "secondary": "C5 (1M x 1M evaluation) and C3 (kde! LOOCV, 100k x 4-D) measured in the same run: key 'secondary'"}
 
 
+# ------------------------------------------------------------------------------------------ secondary workloads ----
+def eval_roofline(label, d, evals, k_ms, dfma, kernel):
+    alg = ALG_SLOTS_EVAL[d]
+    rec = issued_record(label)
+    r = {"bound": "fp64_fma_pipe", "kernel": kernel, "kernel_ms": k_ms, "algorithmic_fp64_slots_per_eval": alg,
+         "achieved": evals * alg * 2 / (k_ms * 1e-3) / 1e12, "peak": dfma * 2 / 1e12, "unit": "TFLOP/s",
+         "frac": evals * alg / (k_ms * 1e-3) / dfma, "issued_fp64_instr_per_eval": None, "issued_frac": None,
+         "traffic": None, "peak_source": "DFMA microbenchmark (kdeb200_pipe_peak) in this run"}
+    if rec:
+        r["issued_fp64_instr_per_eval"] = rec["fp64_lane_instr_per_unit"]
+        r["issued_frac"] = rec["fp64_lane_instr_per_unit"] * evals / (k_ms * 1e-3) / dfma
+        r["traffic_bytes_per_eval_ncu"] = rec["dram_bytes_per_unit"]
+        r["issued_source"] = "profiles/ncu_issued.json[%s] (source hash %s)" % (label, rec["source_hash"])
+    return r
+
+
+def secondary_single(K, dfma, mufu, args):
+    """C5 and C3 on one GPU (N = 1): kernel time via the library's own CUDA-event bracket (kdeb200_last_kernel_ms),
+    end-to-end wall through the host API, CPU port on a bounded sample."""
+    from oracle import oracle as O
+    out = {}
+    cores = host_cores()
+    # ---- C5: brute-force evaluation of a 1M-component 3-D KDE at 1M query points
+    N = M = args.c5_n
+    rng = np.random.default_rng(SEED)
+    pts, pos = mixture(rng, 3, N), mixture(rng, 3, M)
+    bw = silverman(pts)
+    t0 = time.perf_counter(); p = K.kde(pts, bw); t_build = time.perf_counter() - t0
+    K.evaluateDualTree(p, pos[:, :4096])  # H2D of the tree, module warm-up
+    evals = float(N) * M
+    rec = {"workload": "C5: brute-force evaluation, %d components x %d queries, 3-D, Silverman bandwidth" % (N, M),
+           "evals": evals, "tree_build_host_s": t_build}
+    for prec, name in ((K.F64, "f64"), (K.F32, "f32")):
+        t0 = time.perf_counter(); v = K.evaluateDualTree(p, pos, precision=prec); wall = time.perf_counter() - t0
+        ms, nl = K.last_kernel_ms()
+        e = {"value": evals / (ms * 1e-3), "unit": "evals/s", "kernel_ms": ms, "launches": nl,
+             "e2e": {"value": evals / wall, "unit": "evals/s", "wall_s": wall, "h2d_bytes": 8 * 3 * M, "d2h_bytes": 8 * M,
+                     "api": "kde_b200.evaluateDualTree -> kdeb200_eval (host buffers)"}}
+        if prec == K.F64:
+            e["roofline"] = eval_roofline("eval_c5", 3, evals, ms, dfma, "eval_kernel<3,2,false>")
+            ref = v
+        else:
+            e["roofline"] = {"bound": "mufu_ex2", "achieved": evals / (ms * 1e-3) / 1e12, "peak": mufu / 1e12,
+                             "unit": "T ex2/s (1 per eval)", "frac": evals / (ms * 1e-3) / mufu, "kernel": "eval_f32_kernel<3,false>"}
+            e["max_rel_err_vs_f64"] = float(np.max(np.abs(v - ref) / ref))
+        rec[name] = e
+    o = O.OKDE.kde_bw(pts, bw)
+    mq = 128 * cores
+    t0 = time.perf_counter(); ov = o.evaluate(pos[:, :mq], nthreads=cores); tn = time.perf_counter() - t0
+    rec["cpu_baseline"] = {"value": float(N) * mq / tn, "unit": "evals/s", "cores": cores, "kind": "port",
+                           "sample": "%d of %d queries against all %d components in %.1f s (oracle, OpenMP over queries)" % (mq, M, N, tn)}
+    rec["parity_max_rel_err_vs_oracle"] = float(np.max(np.abs(ref[:mq] - ov) / ov))
+    out["c5"] = rec
+    p._invalidate()
+    # ---- C3: kde! LOOCV bandwidth selection on 100k synthetic 4-D mixture points
+    N = args.c3_n
+    pts = mixture(np.random.default_rng(3), 4, N)
+    p1 = K.marginal(K.kde(pts, [1.0]), [1])
+    K.entropy(p1)
+    t0 = time.perf_counter(); H = K.entropy(p1); one = time.perf_counter() - t0
+    ms, nl = K.last_kernel_ms()
+    evals = float(N) * N
+    K.kde(pts[:, :3000])
+    t0 = time.perf_counter(); pk = K.kde(pts); total = time.perf_counter() - t0
+    rec = {"workload": "C3: kde!(points) LOOCV bandwidth selection, %d points, 4-D" % N,
+           "one_nLOO_LL": {"value": evals / (ms * 1e-3), "unit": "evals/s", "kernel_ms": ms, "wall_ms": one * 1e3, "launches": nl,
+                           "H": H, "roofline": eval_roofline("eval_c3", 1, evals, ms, dfma, "eval_kernel<1,6,true>")},
+           "full_kde": {"value": total, "unit": "s", "higher_is_better": False, "bandwidth": K.getBW(pk)[:, 0].tolist(),
+                        "api": "kde_b200.kde(points) -> kdeb200_kde_lcv (host points in, d bandwidths out)",
+                        "h2d_bytes": 8 * 2 * N * 4, "d2h_bytes": 8 * 4}}
+    o1 = O.OKDE.kde_bw(K.getPoints(p1), K.getBW(p1)[:, 0], K.getWeights(p1))
+    mq = 256 * cores
+    t0 = time.perf_counter(); rows = o1.loo_rows(0, mq, nthreads=cores); tn = time.perf_counter() - t0
+    rec["cpu_baseline"] = {"value": float(N) * mq / tn, "unit": "evals/s", "cores": cores, "kind": "port",
+                           "sample": "%d of %d LOO rows of one nLOO_LL in %.2f s (oracle evalDirect rows, OpenMP)" % (mq, N, tn),
+                           "extrapolated_one_nLOO_LL_s": tn * N / mq}
+    out["c3"] = rec
+    return out
+
+
+def secondary_sharded(K, kd, torch, dist, rank, world, dev, args):
+    """C5 with the queries block-partitioned (all-gather of the densities) and C3 with the rows of every nLOO_LL step
+    block-partitioned (all-reduce per step) -- strong scaling, timed as max over ranks."""
+    from kde_b200 import _lib
+    L = _lib.lib()
+    out = {}
+    n = args.c5_n
+    rng = np.random.default_rng(SEED)
+    pts, pos = mixture(rng, 3, n), mixture(rng, 3, n)
+    p = K.kde(pts, silverman(pts))
+    a, b = kd.shard_range(n, rank, world)
+    d_pos = torch.from_numpy(np.ascontiguousarray(pos[:, a:b].T)).to(dev)
+    d_out = torch.empty(b - a, dtype=torch.float64, device=dev)
+    g_out = torch.empty(n, dtype=torch.float64, device=dev)
+
+    def step():
+        _lib.check(L.kdeb200_eval_device(p._dev(), d_pos.data_ptr(), b - a, 0, K.F64, d_out.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream))
+        if n % world == 0:
+            dist.all_gather_into_tensor(g_out, d_out)
+        else:
+            g_out.copy_(kd.all_gather_blocks(d_out, n))
+    step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); step(); step(); e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 2], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # content check: the first 1024 densities of the NEXT rank's block, recomputed here
+    fa, _ = kd.shard_range(n, (rank + 1) % world, world)
+    chk = K.evaluateDualTree(p, pos[:, fa:fa + 1024])
+    ok = torch.tensor([int(np.array_equal(chk, g_out[fa:fa + 1024].cpu().numpy()))], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    out["c5"] = {"workload": "C5: %d components x %d queries, 3-D, f64, queries sharded over %d GPUs + NCCL all-gather" % (n, n, world),
+                 "value": float(n) * n / (float(t.item()) * 1e-3), "unit": "evals/s", "ms_per_call": float(t.item()),
+                 "scaling": "strong", "gather_checked": bool(ok.item())}
+    p._invalidate()
+    n3 = args.c3_n
+    pts = mixture(np.random.default_rng(3), 4, n3)
+    kd.kde_sharded(pts[:, :3000])
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); pk = kd.kde_sharded(pts); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["c3"] = {"workload": "C3: kde!(points) LOOCV, %d points, 4-D, rows of every nLOO_LL step sharded over %d GPUs" % (n3, world),
+                 "full_kde": {"value": float(t.item()), "unit": "s", "higher_is_better": False, "bandwidth": K.getBW(pk)[:, 0].tolist()},
+                 "scaling": "strong"}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------ main ----
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,6 +334,9 @@ def main():
     ap.add_argument("--ref-samples", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C5 / C3 secondary records")
+    ap.add_argument("--c5-n", type=int, default=1_000_000)
+    ap.add_argument("--c3-n", type=int, default=100_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,7 +375,7 @@ def main():
     tree_bytes = 0
     for t in trees:
         b = C.c_int64(0)
-        L.kdeb200_tree_info(t._dev(), None, None, None, C.byref(b))
+        L.kdeb200_tree_info(t._dev(gibbs=True), None, None, None, C.byref(b))
         tree_bytes += b.value
 
     dev = torch.device("cuda", local)
@@ -205,36 +388,72 @@ def main():
         g_pts = torch.empty((Np_total, DIM), dtype=torch.float64, device=dev)
         g_idx = torch.empty((Np_total, NDENS), dtype=torch.int64, device=dev)
 
-    def step():  # the sharded product: this rank's block + NCCL all-gather (kde_b200.dist)
-        _dist.prod_sharded_device(handles, NDENS, DIM, Np_total, NITER, SEED, d_pts, d_idx, g_pts, g_idx)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    time.sleep(0.3)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_wall0 = time.time()
-    for a, b in evs:
-        flush.fill_(1)  # L2 flush, outside the event bracket
-        a.record()
-        step()
-        b.record()
-    barrier()
-    t_wall1 = time.time()
-    ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = float(sum(ms))
-    if world > 1:
-        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
-    clocks = sampler.stop(t_wall0, t_wall1)
+    def timed(step_fn, steps, warmup, sample_clocks=False):
+        """W untimed + K timed steps, CUDA events on the launching stream, L2 flush between steps (outside the bracket),
+        barrier + synchronize on both sides, MAX over ranks."""
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            time.sleep(0.3)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        tw0 = time.time()
+        for a, b in evs:
+            flush.fill_(1)
+            a.record()
+            step_fn()
+            b.record()
+        barrier()
+        tw1 = time.time()
+        tot = float(sum(a.elapsed_time(b) for a, b in evs))
+        if world > 1:
+            tt = torch.tensor([tot], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tot = float(tt.item())
+        return tot, (sampler.stop(tw0, tw1) if sampler else None)
+
+    def gather_check(total, gp, gi):
+        """Recompute GATHER_CHECK samples from the block of rank+1 locally and compare with the gathered rows, bit for bit."""
+        fa, fb = _dist.shard_range(total, (rank + 1) % world, world)
+        n = min(GATHER_CHECK, fb - fa)
+        cp = torch.empty((n, DIM), dtype=torch.float64, device=dev)
+        ci = torch.empty((n, NDENS), dtype=torch.int64, device=dev)
+        _lib.check(L.kdeb200_gibbs_device(handles, NDENS, total, NITER, 1, None, None, 0, None, 0, SEED, fa, fa + n,
+                                          cp.data_ptr(), ci.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        ok = torch.tensor([int(torch.equal(cp, gp[fa:fa + n]) and torch.equal(ci, gi[fa:fa + n]))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return bool(ok.item())
+
+    # ---- headline: weak scaling (1M samples per GPU per step) -------------------------------------------------
+    def step():  # the sharded product: this rank's block + NCCL all-gather (kde_b200.dist)
+        _dist.prod_sharded_device(handles, NDENS, DIM, Np_total, NITER, SEED, d_pts, d_idx, g_pts, g_idx)
+
+    total_ms, clocks = timed(step, args.steps, args.warmup, sample_clocks=True)
     value = Np_total * args.steps / (total_ms * 1e-3)
+    gather_ok = gather_check(Np_total, g_pts, g_idx) if world > 1 else None
+
+    # ---- strong scaling: BASELINE configs[3], 1M samples in total ---------------------------------------------
+    strong = None
+    if world > 1:
+        tot_s = SAMPLES_PER_GPU - SAMPLES_PER_GPU % world
+        a, b = _dist.shard_range(tot_s, rank, world)
+        sp, si = d_pts[: b - a], d_idx[: b - a]
+        gsp, gsi = g_pts[:tot_s], g_idx[:tot_s]
+
+        def step_strong():
+            _dist.prod_sharded_device(handles, NDENS, DIM, tot_s, NITER, SEED, sp, si, gsp, gsi)
+        ms_s, _ = timed(step_strong, args.steps, args.warmup)
+        strong = {"value": tot_s * args.steps / (ms_s * 1e-3), "unit": "samples/s", "ms_per_step": ms_s / args.steps,
+                  "samples_total": tot_s, "samples_per_gpu": b - a, "steps": args.steps, "warmup": args.warmup,
+                  "scaling": "strong", "gather_checked": gather_check(tot_s, gsp, gsi),
+                  "note": "efficiency = value / (n_gpus x the 1-GPU headline value of the same run series)"}
 
     # kernel-only duration for the roofline: same launch, no collective, events on the launch stream
     kms = []
@@ -250,7 +469,8 @@ def main():
         kms.append(a.elapsed_time(b))
     k_ms = float(np.mean(kms))
 
-    # e2e through the host API with host buffers (tree flatten + H2D, D2H of points and labels)
+    # e2e through the host API with host buffers (tree flatten + H2D, D2H of points and labels).  At N > 1 this is the
+    # "consumer is host memory" variant of SURVEY.md 8e: every rank copies its own shard straight to the host, no gather.
     e2e_n = n_per
     e2e_t = []
     for i in range(1 + max(1, min(args.steps, 2))):
@@ -271,8 +491,17 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_dt = float(tt.item())
     e2e_val = e2e_n * world / e2e_dt
+    handles = _api._handles(trees)  # the e2e leg rebuilt the device trees
 
-    out = None
+    secondary = None
+    if not args.no_secondary:
+        if world > 1:
+            secondary = secondary_sharded(K, _dist, torch, dist, rank, world, dev, args)
+        elif rank == 0:
+            dfma0, _ = K.pipe_peak(0, 200000)
+            mufu0, _ = K.pipe_peak(2, 200000)
+            secondary = secondary_single(K, dfma0, mufu0, args)
+
     if rank == 0:
         # roofline denominators measured live: dependency-free DFMA stream
         dfma, _ = K.pipe_peak(0, 200000)
@@ -282,26 +511,30 @@ def main():
             peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        alg_bytes = tree_bytes + n_per * (DIM * 8 + NDENS * 8)
+        rec = issued_record("gibbs_c4")
         roof = {"bound": "fp64_fma_pipe", "achieved": ach * 2 / 1e12, "peak": dfma * 2 / 1e12, "unit": "TFLOP/s",
-                "frac": ach / dfma, "traffic": None,
-                "traffic_note": "ncu --set full on a 75,776-sample launch of the same kernel (profiles/r01_gibbs_v9_ncu.txt): "
-                                "dram read 0.19 GB + write 1.88 GB (local-memory checkpoints leaving L2), i.e. ~27 KB/sample "
-                                "or <0.5% of HBM bandwidth; a full 1M-sample launch does not finish under ncu replay",
-                "kernel": "gibbs_kernel<3,false>", "kernel_ms": k_ms,
-                # honest "issued" view next to the algorithmic one (SURVEY.md 8d asks for both): the kernel issues
-                # 13.1e6 FP64 instructions per sample (ncu, profiles/r01_gibbs_v9_ncu.txt) -- fewer than the model's
-                # 17.9e6 slots because exp costs 7 instructions instead of 14 -- so frac can exceed 1
-                "issued_fp64_instr_per_sample": ISSUED_FP64_PER_SAMPLE,
-                "issued_frac": ISSUED_FP64_PER_SAMPLE * n_per / (k_ms * 1e-3) / dfma,
+                "frac": ach / dfma, "kernel": "gibbs_kernel<3,false>", "kernel_ms": k_ms,
+                # DRAM bytes of ONE launch (ncu dram__bytes_read + write, scaled per sample to this launch's samples)
+                "traffic": None, "traffic_ratio": None, "algorithmic_bytes": alg_bytes,
+                # honest "issued" view next to the algorithmic one (SURVEY.md 8d asks for both): the kernel issues fewer
+                # FP64 instructions per sample than the model's 17.9e6 slots (exp costs 7 instead of 14), so frac can exceed 1
+                "issued_fp64_instr_per_sample": None, "issued_frac": None,
                 "algorithmic_fp64_slots_per_sample": ALG_SLOTS_PER_SAMPLE, "kernel_evals_per_sample": evals,
                 "peak_source": "DFMA microbenchmark (kdeb200_pipe_peak) measured in this run; nominal 64/clk/SM x 148 x 1.965 GHz = 37.2 TFLOP/s",
-                # the HBM view of the same launch, for the record: compulsory bytes = trees in + points and labels out
-                "hbm_view": {"algorithmic_bytes": tree_bytes + n_per * (DIM * 8 + NDENS * 8),
-                             "achieved_GBs": (tree_bytes + n_per * (DIM * 8 + NDENS * 8)) / (k_ms * 1e-3) / 1e9,
+                "hbm_view": {"algorithmic_bytes": alg_bytes, "achieved_GBs": alg_bytes / (k_ms * 1e-3) / 1e9,
                              "peak_GBs": peaks_file.get("hbm_gbs"),
-                             "frac": ((tree_bytes + n_per * (DIM * 8 + NDENS * 8)) / (k_ms * 1e-3) / 1e9 / peaks_file["hbm_gbs"])
-                             if peaks_file.get("hbm_gbs") else None},
-                "note": "path is FP64-FMA-pipe bound, not HBM/tensor (SURVEY.md 8d): the HBM view above is ~1e-5 of the measured copy bandwidth"}
+                             "frac": (alg_bytes / (k_ms * 1e-3) / 1e9 / peaks_file["hbm_gbs"]) if peaks_file.get("hbm_gbs") else None},
+                "note": "path is FP64-FMA-pipe bound, not HBM/tensor (SURVEY.md 8d): the HBM view is ~1e-5 of the measured copy bandwidth"}
+        if rec:
+            roof["issued_fp64_instr_per_sample"] = rec["fp64_lane_instr_per_unit"]
+            roof["issued_other_instr_per_sample"] = rec["other_lane_instr_per_unit"]
+            roof["issued_frac"] = rec["fp64_lane_instr_per_unit"] * n_per / (k_ms * 1e-3) / dfma
+            roof["traffic"] = rec["dram_bytes_per_unit"] * n_per
+            roof["traffic_ratio"] = roof["traffic"] / alg_bytes
+            roof["traffic_source"] = ("profiles/ncu_issued.json[gibbs_c4]: dram__bytes_read+write of a %d-sample launch "
+                                      "(source hash %s), scaled per sample" % (int(rec["units_per_launch"]), rec["source_hash"]))
+            roof["fp64_pipe_active_pct_ncu"] = rec["fp64_pipe_active_pct"]
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             from oracle import oracle as O
@@ -330,12 +563,13 @@ def main():
             "metric": "product samples/sec (Gibbs, Niter=5)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(), "clocks": clocks,
+            "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": tree_bytes,
                     "d2h_bytes_per_step": e2e_n * (DIM * 8 + NDENS * 8), "ms_per_step": e2e_dt * 1e3,
-                    "api": "kde_b200.prodAppxMSGibbsS -> kdeb200_tree_create x8 + kdeb200_gibbs (host buffers)"},
+                    "api": "kde_b200.prodAppxMSGibbsS -> kdeb200_tree_create x8 + kdeb200_gibbs (host buffers; at N > 1 every "
+                           "rank copies its own shard to the host: the no-gather variant of SURVEY.md 8e)"},
             "gpu_launches": args.steps, "roofline": roof, "cpu_baseline": cpu,
-            "kernel_evals_per_s": evals * value,
+            "kernel_evals_per_s": evals * value, "strong": strong, "gather_checked": gather_ok, "secondary": secondary,
         }
         print(json.dumps(out))
     if world > 1:

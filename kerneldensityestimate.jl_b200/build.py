@@ -14,6 +14,26 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-ccbin", "/usr/bin/g++", "-Xptxas", "-v"]
 
 
+# the sources that determine each hot kernel's instruction stream (tools/ncu_issued.py keys its ncu counters by this
+# hash; bench.py refuses to quote issued-instruction numbers measured on other sources)
+KERNEL_SOURCES = {
+    "gibbs": ["gibbs_kernel.cuh", "gibbs.cu", "common.cuh", "tree.cuh"],
+    "eval": ["eval.cu", "eval_shared.cuh", "common.cuh", "tree.cuh"],
+    "eval_f32": ["eval_f32.cu", "common.cuh", "tree.cuh"],
+    "lcv": ["lcv.cu", "eval_shared.cuh", "common.cuh", "tree.cuh"],
+}
+
+
+def kernel_source_hash(kind):
+    import hashlib
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES[kind]:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def _stale():
     if not os.path.exists(OUT):
         return True

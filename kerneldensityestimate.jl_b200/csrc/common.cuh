@@ -33,6 +33,7 @@ const char *get_error();
 struct Context {
   bool ready = false;
   int device = 0;
+  int slot = 0;  // 0 = primary, 1.. = the other GPUs of the in-process multi-GPU set
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   double *d_exptab = nullptr;  // KDE_EXP_TAB entries of 2^(j/TAB), high word biased (kde_exp_core)
@@ -40,8 +41,20 @@ struct Context {
   double last_ms = 0.0;
   int last_launches = 0;
 };
-Context &ctx();
+Context &ctx();           // the context bound to this host thread (ScopedDevice), else the primary
+Context &ctx_at(int slot);
+int multi_count();        // GPUs in the in-process set (1 unless kdeb200_init_multi was called)
 int ensure_init();
+// Binds the calling host thread to the context of `slot` (cudaSetDevice + ctx()) for the scope's lifetime.
+struct ScopedDevice {
+  explicit ScopedDevice(int slot);
+  ~ScopedDevice();
+  ScopedDevice(const ScopedDevice &) = delete;
+  ScopedDevice &operator=(const ScopedDevice &) = delete;
+ private:
+  void *prev_;
+  int prev_dev_ = 0;
+};
 
 // ---------------------------------------------------------------- Philox4x32-10 ---------
 // Counter-based generator (Salmon et al., SC'11).  Streams are addressed as

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -19,34 +20,47 @@ void set_error(const char *fmt, ...) {
 }
 const char *get_error() { return g_err; }
 
-Context &ctx() {
-  static Context c;
-  return c;
+// Slot 0 is the primary context (the device the process is bound to: kdeb200_init / first use); slots 1.. are the
+// other GPUs of an in-process multi-GPU set (kdeb200_init_multi).  A host thread that drives one of them binds it with
+// ScopedDevice; ctx() then returns that context, so every internal routine works unchanged on any device.
+static Context g_ctx[KDEB200_MAX_GPUS];
+static int g_nctx = 1;
+static thread_local Context *tl_ctx = nullptr;
+
+Context &ctx() { return tl_ctx ? *tl_ctx : g_ctx[0]; }
+Context &ctx_at(int slot) { return g_ctx[slot]; }
+int multi_count() { return (g_ctx[0].ready && g_nctx > 1) ? g_nctx : 1; }
+
+ScopedDevice::ScopedDevice(int slot) : prev_(tl_ctx) {
+  cudaGetDevice(&prev_dev_);
+  tl_ctx = &g_ctx[slot];
+  cudaSetDevice(g_ctx[slot].device);
+}
+ScopedDevice::~ScopedDevice() {
+  tl_ctx = static_cast<Context *>(prev_);
+  cudaSetDevice(prev_dev_);
 }
 
 static std::mutex g_mu;
 
-static int init_device(int device) {
-  Context &c = ctx();
-  int count = 0;
-  KDE_CUDA(cudaGetDeviceCount(&count));
-  if (count <= 0) KDE_FAIL(20, "no CUDA device visible: libkdeb200 has no CPU fallback");
-  if (device < 0 || device >= count) KDE_FAIL(21, "kdeb200_init: device %d out of range (0..%d)", device, count - 1);
+static void drop_context(Context &c) {
+  if (!c.ready) return;
+  cudaSetDevice(c.device);
+  cudaStreamSynchronize(c.stream);
+  cudaFree(c.d_exptab);
+  cudaEventDestroy(c.ev0);
+  cudaEventDestroy(c.ev1);
+  cudaStreamDestroy(c.stream);
+  c = Context();
+}
+
+static int make_context(Context &c, int device, int slot) {
   KDE_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   KDE_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) KDE_FAIL(22, "libkdeb200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
-  if (c.ready && c.device == device) return 0;
-  if (c.ready) {  // re-bind
-    cudaSetDevice(c.device);
-    cudaFree(c.d_exptab);
-    cudaEventDestroy(c.ev0);
-    cudaEventDestroy(c.ev1);
-    cudaStreamDestroy(c.stream);
-    c.ready = false;
-    KDE_CUDA(cudaSetDevice(device));
-  }
   c.device = device;
+  c.slot = slot;
   c.sm_count = prop.multiProcessorCount;
   KDE_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   {  // keep up to 1 GiB of freed blocks in the stream-ordered pool (the default returns everything to the driver
@@ -69,6 +83,63 @@ static int init_device(int device) {
   KDE_CUDA(cudaMalloc(&c.d_exptab, sizeof(tab)));
   KDE_CUDA(cudaMemcpy(c.d_exptab, tab, sizeof(tab), cudaMemcpyHostToDevice));
   c.ready = true;
+  return 0;
+}
+
+static int init_device(int device) {
+  Context &c = g_ctx[0];
+  int count = 0;
+  KDE_CUDA(cudaGetDeviceCount(&count));
+  if (count <= 0) KDE_FAIL(20, "no CUDA device visible: libkdeb200 has no CPU fallback");
+  if (device < 0 || device >= count) KDE_FAIL(21, "kdeb200_init: device %d out of range (0..%d)", device, count - 1);
+  if (c.ready && c.device == device) {
+    KDE_CUDA(cudaSetDevice(device));
+    return 0;
+  }
+  for (int s = g_nctx - 1; s >= 0; --s) drop_context(g_ctx[s]);  // re-bind: the multi-GPU set goes with it
+  g_nctx = 1;
+  return make_context(c, device, 0);
+}
+
+// The primary plus the next visible devices (in index order) until `ngpus` contexts exist; ngpus <= 0: every visible device.
+static int init_multi(int ngpus) {
+  int count = 0;
+  KDE_CUDA(cudaGetDeviceCount(&count));
+  if (count <= 0) KDE_FAIL(20, "no CUDA device visible: libkdeb200 has no CPU fallback");
+  if (ngpus <= 0) ngpus = count;
+  if (ngpus > count) KDE_FAIL(21, "kdeb200_init_multi: %d GPUs requested, %d visible", ngpus, count);
+  if (ngpus > KDEB200_MAX_GPUS) KDE_FAIL(21, "kdeb200_init_multi: at most %d GPUs", KDEB200_MAX_GPUS);
+  if (!g_ctx[0].ready) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    if (int rc = init_device(dev)) return rc;
+  }
+  for (int s = g_nctx - 1; s >= ngpus; --s) drop_context(g_ctx[s]);  // shrinking
+  if (g_nctx > ngpus) g_nctx = ngpus;
+  int dev = 0;
+  std::vector<char> used(count, 0);
+  for (int s = 0; s < g_nctx; ++s) used[g_ctx[s].device] = 1;
+  while (g_nctx < ngpus) {
+    while (dev < count && used[dev]) ++dev;
+    if (int rc = make_context(g_ctx[g_nctx], dev, g_nctx)) {
+      cudaSetDevice(g_ctx[0].device);
+      return rc;
+    }
+    used[dev] = 1;
+    ++g_nctx;
+  }
+  for (int a = 0; a < g_nctx; ++a)  // peer access for the tree replication copies (ignored where unsupported)
+    for (int b = 0; b < g_nctx; ++b) {
+      if (a == b) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, g_ctx[a].device, g_ctx[b].device);
+      if (can) {
+        cudaSetDevice(g_ctx[a].device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(g_ctx[b].device, 0);
+        if (e != cudaSuccess) cudaGetLastError();  // already enabled
+      }
+    }
+  KDE_CUDA(cudaSetDevice(g_ctx[0].device));
   return 0;
 }
 
@@ -108,17 +179,21 @@ int kdeb200_init(int device) {
   return init_device(device);
 }
 
+int kdeb200_init_multi(int ngpus) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return init_multi(ngpus);
+}
+
+int kdeb200_multi_count(int *ngpus) {
+  if (!ngpus) KDE_FAIL(2, "multi_count: NULL");
+  *ngpus = multi_count();
+  return 0;
+}
+
 int kdeb200_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
-  Context &c = ctx();
-  if (!c.ready) return 0;
-  cudaSetDevice(c.device);
-  cudaStreamSynchronize(c.stream);
-  cudaFree(c.d_exptab);
-  cudaEventDestroy(c.ev0);
-  cudaEventDestroy(c.ev1);
-  cudaStreamDestroy(c.stream);
-  c = Context();
+  for (int s = g_nctx - 1; s >= 0; --s) drop_context(g_ctx[s]);
+  g_nctx = 1;
   return 0;
 }
 

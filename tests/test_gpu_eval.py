@@ -327,9 +327,13 @@ def test_update_bandwidth_invalidates_the_device_records():
     assert relerr(K.evaluateDualTree(p, p), K.evaluateDualTree(fresh, fresh)) < 1e-13
     assert relerr(p(pos), K.evaluateDualTree(fresh, pos)) < 1e-13
     assert abs(K.entropy(p) - K.entropy(fresh)) < 1e-13 * abs(K.entropy(fresh))
+    # Gibbs reads the INTERNAL nodes' variances too, and updateBandwidth! scales those as well (2.25 x (h^2 + spread),
+    # not what kde!(pts, 1.5 h) builds): compare with a density object assembled from the very same scaled arrays
+    same = K.BallTreeDensity(p.bt, p.means.copy(), p.bandwidth.copy())
     g1 = K.prodAppxMSGibbsS(None, [p, p], None, None, Niter=2, Np=128, seed=9)
-    g2 = K.prodAppxMSGibbsS(None, [fresh, fresh], None, None, Niter=2, Np=128, seed=9)
-    assert np.array_equal(g1[1], g2[1]) and np.max(np.abs(g1[0] - g2[0])) < 1e-12
+    g2 = K.prodAppxMSGibbsS(None, [same, same], None, None, Niter=2, Np=128, seed=9)
+    g3 = K.prodAppxMSGibbsS(None, [fresh, fresh], None, None, Niter=2, Np=128, seed=9)
+    assert np.array_equal(g1[1], g2[1]) and np.array_equal(g1[0], g2[0]) and not np.array_equal(g1[1], g3[1])
     # nLOO_LL's multiply / divide-back leaves the (ulp-drifted) bandwidth in place and later calls see it
     H = K.nLOO_LL(1.3, p)
     o = OKDE.kde_bw(pts, [0.45, 0.6])
