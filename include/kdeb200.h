@@ -32,6 +32,7 @@ extern "C" {
 
 #define KDEB200_MAX_DIM 8
 #define KDEB200_MAX_DENS 16
+#define KDEB200_MAX_GPUS 16
 
 #define KDEB200_F64 0 /* FP64 arithmetic (parity mode: 1e-12 eval, exact labels) */
 #define KDEB200_F32 1 /* FP32 arithmetic with MUFU ex2 (evaluation only, 1e-5) */
@@ -44,6 +45,19 @@ int kdeb200_version(void);
 int kdeb200_device_count(int *count);
 /* Binds the calling process to CUDA device `device` (one process per GPU). */
 int kdeb200_init(int device);
+/* In-process multi-GPU: one host process drives `ngpus` devices (<= 0: every visible one;
+ * the device bound by kdeb200_init, or device 0, stays the primary).  Afterwards the HOST-BUFFER entry points
+ * kdeb200_gibbs, kdeb200_eval, kdeb200_loo_entropy and kdeb200_kde_lcv shard their independent units (samples, query
+ * points, leaf rows) over the set: trees are replicated to every device on first use (peer copies over NVLink), each
+ * device runs its block on its own stream from its own host thread and copies its shard straight into the caller's
+ * host buffer -- no gather and no collective, because the consumer is host memory.  Results do not depend on the
+ * number of GPUs (units are addressed by global index; likelihood partials are summed in block order).  The
+ * *_device entry points keep running on the device that owns their pointers.  kdeb200_init_multi(1) switches back. */
+int kdeb200_init_multi(int ngpus);
+/* Explicit device list (devices[0] = primary).  A device may be listed more than once: several contexts then share
+ * that GPU (no speed-up; exercises the whole sharding path on a single-GPU box). */
+int kdeb200_init_multi_devices(const int *devices, int n);
+int kdeb200_multi_count(int *ngpus);
 int kdeb200_shutdown(void);
 int kdeb200_device_props(int *sm_count, int *cc_major, int *cc_minor, int *clock_khz, size_t *free_bytes);
 
@@ -145,6 +159,14 @@ typedef int (*kdeb200_allreduce_fn)(double *sum, int *zero_flag, void *user);
 int kdeb200_kde_lcv_sharded(int d, int64_t N, const double *points, int64_t j0, int64_t j1,
                             kdeb200_allreduce_fn allreduce, void *user, double *bw_std_out,
                             int *nloo_calls_out);
+/* Vector form of the exchange: the d golden-section searches advance in lock-step (every step evaluates the current
+ * alpha of every unfinished dimension, the launches of all dimensions queued back to back), so ONE call
+ * allreduce(sums, zero_flags, count, user) per step carries the `count` (<= d) partial likelihoods and flags of that
+ * step -- one small all-reduce instead of d.  Same bandwidths as the scalar form. */
+typedef int (*kdeb200_allreduce_v_fn)(double *sums, int *zero_flags, int count, void *user);
+int kdeb200_kde_lcv_sharded_v(int d, int64_t N, const double *points, int64_t j0, int64_t j1,
+                              kdeb200_allreduce_v_fn allreduce, void *user, double *bw_std_out,
+                              int *nloo_calls_out);
 
 /* ---- measurement ----------------------------------------------------------------------------
  * Pipe-rate microbenchmarks for the roofline denominators: dependent-free DFMA,

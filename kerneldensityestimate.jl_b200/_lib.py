@@ -15,12 +15,16 @@ tree_t = C.c_void_p
 
 # name -> (restype, argtypes); kept in sync with include/kdeb200.h (tests/test_abi.py checks it)
 allreduce_fn = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p)
+allreduce_v_fn = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int, C.c_void_p)
 
 SIGNATURES = {
     "kdeb200_last_error": (C.c_char_p, []),
     "kdeb200_version": (C.c_int, []),
     "kdeb200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "kdeb200_init": (C.c_int, [C.c_int]),
+    "kdeb200_init_multi": (C.c_int, [C.c_int]),
+    "kdeb200_init_multi_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "kdeb200_multi_count": (C.c_int, [C.POINTER(C.c_int)]),
     "kdeb200_shutdown": (C.c_int, []),
     "kdeb200_device_props": (C.c_int, [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_size_t)]),
     "kdeb200_tree_create": (C.c_int, [C.c_int, C.c_int64, f64p, f64p, f64p, i64p, i64p, i64p, C.POINTER(tree_t)]),
@@ -43,6 +47,8 @@ SIGNATURES = {
     "kdeb200_kde_lcv": (C.c_int, [C.c_int, C.c_int64, f64p, f64p, C.POINTER(C.c_int)]),
     "kdeb200_kde_lcv_sharded": (C.c_int, [C.c_int, C.c_int64, f64p, C.c_int64, C.c_int64, allreduce_fn, C.c_void_p, f64p,
                                           C.POINTER(C.c_int)]),
+    "kdeb200_kde_lcv_sharded_v": (C.c_int, [C.c_int, C.c_int64, f64p, C.c_int64, C.c_int64, allreduce_v_fn, C.c_void_p, f64p,
+                                            C.POINTER(C.c_int)]),
     "kdeb200_pipe_peak": (C.c_int, [C.c_int, C.c_int, f64p, f64p]),
     "kdeb200_dfma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, f64p]),
     "kdeb200_last_kernel_ms": (C.c_int, [f64p, C.POINTER(C.c_int)]),

@@ -28,7 +28,7 @@ from ._lib import KDEError, check, fptr, iptr, lib
 __all__ = [
     "KDEError", "BallTree", "BallTreeDensity", "kde", "kde_bang", "getPoints", "getBW", "getWeights", "marginal",
     "sample", "rand", "resample", "evaluateDualTree", "evalAvgLogL", "entropy", "kld", "minkld", "nLOO_LL", "golden",
-    "ksize", "neighborMinMax", "lcv_bandwidths", "updateBandwidth", "prodAppxMSGibbsS", "Ndim", "Npts", "init", "gibbs_sizes",
+    "ksize", "neighborMinMax", "lcv_bandwidths", "updateBandwidth", "prodAppxMSGibbsS", "Ndim", "Npts", "init", "init_multi", "multi_count", "gibbs_sizes",
     "philox_streams", "pipe_peak", "last_kernel_ms", "F64", "F32", "prod", "getKDERange", "getKDERangeLinspace",
     "getKDEMax", "getKDEMean", "getKDEfit", "intersIntgAppxIS", "to_string", "from_string",
 ]
@@ -40,6 +40,24 @@ _EUCLID = ("+", "-")
 def init(device=0):
     """Bind this process to one GPU (one process per GPU)."""
     check(lib().kdeb200_init(int(device)))
+
+
+def init_multi(ngpus=0, devices=None):
+    """In-process multi-GPU (kdeb200_init_multi): afterwards prodAppxMSGibbsS, evaluateDualTree, entropy and
+    kde(points) shard their samples / query points / leaf rows over `ngpus` devices of this process (0 = all visible).
+    devices = explicit list (devices[0] = primary; repeats allowed, see include/kdeb200.h).  Returns the set's size."""
+    if devices is not None:
+        arr = (C.c_int * len(devices))(*[int(x) for x in devices])
+        check(lib().kdeb200_init_multi_devices(arr, len(devices)))
+    else:
+        check(lib().kdeb200_init_multi(int(ngpus)))
+    return multi_count()
+
+
+def multi_count():
+    n = C.c_int(0)
+    check(lib().kdeb200_multi_count(C.byref(n)))
+    return n.value
 
 
 def _require_euclidean(**ops):

@@ -4,6 +4,8 @@
 #include <cmath>
 #include <limits>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "tree.cuh"
@@ -16,7 +18,7 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
                 const int64_t *left, const int64_t *right, const int64_t *perm, bool gibbs_records,
                 kdeb200_tree_t *out);
 int tree_destroy(kdeb200_tree_t t);
-int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb200_allreduce_fn allreduce, void *user,
+int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb200_allreduce_v_fn allreduce, void *user,
             double *bw_std_out, int *ncalls_out);
 int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int64_t q0, bool scatter,
                 const double *bw_var, double *d_out, cudaStream_t st, int *launches);
@@ -67,6 +69,167 @@ struct Timer {  // CUDA-event bracket on the library stream, result readable via
     c.last_ms = ms;
   }
 };
+
+// ---- in-process multi-GPU: block partition + one host thread per device --------------------------------------------
+static inline void shard_range(int64_t n, int g, int G, int64_t &a, int64_t &b) {  // first n % G blocks get one extra unit
+  const int64_t base = n / G, rem = n % G;
+  a = g * base + (g < rem ? g : rem);
+  b = a + base + (g < rem ? 1 : 0);
+}
+
+// GPUs to use for `units` independent units when each GPU should get at least `min_per_gpu`
+static inline int gpus_for(int64_t units, int64_t min_per_gpu) {
+  int G = multi_count();
+  if (G > 1 && units < (int64_t)G * min_per_gpu) G = (int)(units / min_per_gpu);
+  return G < 1 ? 1 : G;
+}
+
+// fn(slot) on slots 0..G-1: slot 0 on the calling thread, the others on their own host threads bound to their device.
+// Error strings are thread-local, so the first failing worker's message is copied to the caller.
+template <class F>
+static int for_each_gpu(int G, F fn) {
+  if (G <= 1) return fn(0);
+  std::vector<int> rc(G, 0);
+  std::vector<std::string> err(G);
+  std::vector<std::thread> th;
+  for (int g = 1; g < G; ++g)
+    th.emplace_back([&, g] {
+      ScopedDevice sd(g);
+      rc[g] = fn(g);
+      if (rc[g]) err[g] = get_error();
+    });
+  {
+    ScopedDevice sd(0);
+    rc[0] = fn(0);
+    if (rc[0]) err[0] = get_error();
+  }
+  for (auto &t : th) t.join();
+  for (int g = 0; g < G; ++g)
+    if (rc[g]) {
+      set_error("GPU slot %d: %s", g, err[g].c_str());
+      return rc[g];
+    }
+  return 0;
+}
+
+// samples [a, b) of the run on the GPU of the calling thread's context: staging, launch, D2H into the caller's buffers
+// (points_out / indices_out / level_labels_out point at sample a's slot)
+static int gibbs_host_block(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
+                            const uint8_t *dimmask, const double *randU, const double *randN, uint64_t seed, int64_t a,
+                            int64_t b, int L, int64_t perU, int64_t perN, double *points_out, int64_t *indices_out,
+                            int64_t *level_labels_out, double *ms_out, int *launches_out) {
+  Context &c = ctx();
+  const int d = trees[0]->d;
+  const int64_t n = b - a;
+  if (n <= 0) return 0;
+  kdeb200_tree_t loc[KDEB200_MAX_DENS];
+  for (int j = 0; j < ndens; ++j)
+    if (int rc = tree_on(trees[j], c.slot, &loc[j])) return rc;
+  DevBuf dU(c.stream), dN(c.stream), dP(c.stream), dI(c.stream), dR(c.stream);
+  if (randU) {
+    // only the slices this range touches travel: [a*perU - 1, b*perU - 1) and [a*perN, b*perN)
+    KDE_CUDA(dU.alloc(sizeof(double) * n * perU));
+    KDE_CUDA(dN.alloc(sizeof(double) * n * perN));
+    const int64_t ulo = a * perU > 0 ? a * perU - 1 : 0;  // slot -1 of sample 0 is never read
+    const int64_t skip = a * perU > 0 ? 0 : 1;
+    KDE_CUDA(cudaMemcpyAsync(dU.as<double>() + skip, randU + ulo, sizeof(double) * (n * perU - skip),
+                             cudaMemcpyHostToDevice, c.stream));
+    KDE_CUDA(cudaMemcpyAsync(dN.p, randN + a * perN, sizeof(double) * n * perN, cudaMemcpyHostToDevice, c.stream));
+  }
+  KDE_CUDA(dP.alloc(sizeof(double) * d * n));
+  KDE_CUDA(dI.alloc(sizeof(int64_t) * ndens * n));
+  int64_t *d_rec = nullptr;
+  if (level_labels_out) {  // never-written entries (Niter == 0) stay -1
+    KDE_CUDA(dR.alloc(sizeof(int64_t) * ndens * n * L));
+    KDE_CUDA(cudaMemsetAsync(dR.p, 0xFF, sizeof(int64_t) * ndens * n * L, c.stream));
+    d_rec = dR.as<int64_t>();
+  }
+  Timer tm(c);
+  int launches = 0;
+  int rc;
+  if (randU) {
+    // device slices are re-based: sample s reads U[(s-a)*perU + c - 1 + 1] => pass pointer + 1
+    rc = gibbs_device(loc, ndens, n, Niter, add_entropy, dimmask, dU.as<double>() + 1, n * perU - 1, dN.as<double>(),
+                      n * perN, seed, 0, n, dP.as<double>(), dI.as<int64_t>(), d_rec, c.stream, &launches);
+  } else {
+    rc = gibbs_device(loc, ndens, Np, Niter, add_entropy, dimmask, nullptr, 0, nullptr, 0, seed, a, b, dP.as<double>(),
+                      dI.as<int64_t>(), d_rec, c.stream, &launches);
+  }
+  if (rc) return rc;
+  tm.stop();
+  c.last_launches = launches;
+  if (ms_out) *ms_out = c.last_ms;
+  if (launches_out) *launches_out = launches;
+  KDE_CUDA(cudaMemcpyAsync(points_out, dP.p, sizeof(double) * d * n, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaMemcpyAsync(indices_out, dI.p, sizeof(int64_t) * ndens * n, cudaMemcpyDeviceToHost, c.stream));
+  if (level_labels_out)
+    KDE_CUDA(cudaMemcpyAsync(level_labels_out, dR.p, sizeof(int64_t) * ndens * n * L, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+// query rows [a, b) on the calling thread's GPU; LOO rows come back in LEAF order (the caller scatters through h_perm)
+static int eval_host_block(kdeb200_tree_t bd, const double *pos, int64_t a, int64_t b, int loo, int precision,
+                           bool scatter, double *out_block, double *ms_out, int *launches_out) {
+  Context &c = ctx();
+  const int64_t n = b - a;
+  if (n <= 0) return 0;
+  kdeb200_tree_t loc;
+  if (int rc = tree_on(bd, c.slot, &loc)) return rc;
+  DevBuf dQ(c.stream), dO(c.stream);
+  if (!loo) {
+    KDE_CUDA(dQ.alloc(sizeof(double) * bd->d * n));
+    KDE_CUDA(cudaMemcpyAsync(dQ.p, pos + a * bd->d, sizeof(double) * bd->d * n, cudaMemcpyHostToDevice, c.stream));
+  }
+  KDE_CUDA(dO.alloc(sizeof(double) * n));
+  Timer tm(c);
+  int launches = 0;
+  int rc = (precision == KDEB200_F64)
+               ? eval_device(loc, dQ.as<double>(), n, loo, a, scatter, nullptr, dO.as<double>(), c.stream, &launches)
+               : eval_device_f32(loc, dQ.as<double>(), n, loo, dO.as<double>(), c.stream, &launches);
+  if (rc) return rc;
+  tm.stop();
+  c.last_launches = launches;
+  if (ms_out) *ms_out = c.last_ms;
+  if (launches_out) *launches_out = launches;
+  KDE_CUDA(cudaMemcpyAsync(out_block, dO.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+static int loo_partial_block(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int64_t j1, double *sum_out,
+                             int *zero_flag_out, double *ms_out, int *launches_out) {
+  Context &c = ctx();
+  *sum_out = 0.0;
+  *zero_flag_out = 0;
+  if (j0 >= j1) return 0;
+  kdeb200_tree_t loc;
+  if (int rc = tree_on(bd, c.slot, &loc)) return rc;
+  DevBuf dS(c.stream), dF(c.stream);
+  KDE_CUDA(dS.alloc(sizeof(double)));
+  KDE_CUDA(dF.alloc(sizeof(int)));
+  Timer tm(c);
+  int launches = 0;
+  if (int rc = loo_partial_device(loc, bw_var, j0, j1, dS.as<double>(), dF.as<int>(), c.stream, &launches)) return rc;
+  tm.stop();
+  c.last_launches = launches;
+  if (ms_out) *ms_out = c.last_ms;
+  if (launches_out) *launches_out = launches;
+  KDE_CUDA(cudaMemcpyAsync(sum_out, dS.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaMemcpyAsync(zero_flag_out, dF.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+// kernel time of a sharded call = the slowest device; launches = the sum
+static void publish_timing(const std::vector<double> &ms, const std::vector<int> &launches) {
+  double m = 0.0;
+  int l = 0;
+  for (double v : ms) m = v > m ? v : m;
+  for (int v : launches) l += v;
+  ctx_at(0).last_ms = m;
+  ctx_at(0).last_launches = l;
+}
 }  // namespace kdeb200
 
 using namespace kdeb200;
@@ -142,7 +305,6 @@ int kdeb200_gibbs(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter,
   KDE_SERIALISE();
   if (int rc = ensure_init()) return rc;
   if (!trees || !points_out || !indices_out) KDE_FAIL(2, "gibbs: NULL argument");
-  Context &c = ctx();
   int L;
   int64_t perU, perN;
   if (int rc = gibbs_sizes(trees, ndens, Niter, &L, &perU, &perN, nullptr)) return rc;
@@ -150,49 +312,27 @@ int kdeb200_gibbs(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter,
   const int d = trees[0]->d;
   const int64_t n = s1 - s0;
   if (n == 0) return 0;
-  DevBuf dU(c.stream), dN(c.stream), dP(c.stream), dI(c.stream);
   if ((randU == nullptr) != (randN == nullptr)) KDE_FAIL(3, "gibbs: randU and randN must be given together");
   if (randU) {
-    // only the slices this range touches travel: [s0*perU - 1, s1*perU - 1) and [s0*perN, s1*perN)
     if (s1 * perU > nU + 1) KDE_FAIL(7, "gibbs: randU too short (%lld < %lld)", (long long)nU, (long long)(s1 * perU - 1));
     if (s1 * perN > nN) KDE_FAIL(7, "gibbs: randN too short (%lld < %lld)", (long long)nN, (long long)(s1 * perN));
-    KDE_CUDA(dU.alloc(sizeof(double) * n * perU));
-    KDE_CUDA(dN.alloc(sizeof(double) * n * perN));
-    const int64_t ulo = s0 * perU > 0 ? s0 * perU - 1 : 0;  // slot -1 of sample 0 is never read
-    const int64_t skip = s0 * perU > 0 ? 0 : 1;
-    KDE_CUDA(cudaMemcpyAsync(dU.as<double>() + skip, randU + ulo, sizeof(double) * (n * perU - skip),
-                             cudaMemcpyHostToDevice, c.stream));
-    KDE_CUDA(cudaMemcpyAsync(dN.p, randN + s0 * perN, sizeof(double) * n * perN, cudaMemcpyHostToDevice, c.stream));
   }
-  KDE_CUDA(dP.alloc(sizeof(double) * d * n));
-  KDE_CUDA(dI.alloc(sizeof(int64_t) * ndens * n));
-  DevBuf dR(c.stream);
-  int64_t *d_rec = nullptr;
-  if (level_labels_out) {  // never-written entries (Niter == 0) stay -1
-    KDE_CUDA(dR.alloc(sizeof(int64_t) * ndens * n * L));
-    KDE_CUDA(cudaMemsetAsync(dR.p, 0xFF, sizeof(int64_t) * ndens * n * L, c.stream));
-    d_rec = dR.as<int64_t>();
-  }
-  Timer tm(c);
-  int launches = 0;
-  int rc;
-  if (randU) {
-    // device slices are re-based: sample s reads U[(s-s0)*perU + c - 1 + 1] => pass pointer + 1
-    rc = gibbs_device(trees, ndens, n, Niter, add_entropy, dimmask, dU.as<double>() + 1, n * perU - 1,
-                      dN.as<double>(), n * perN, seed, 0, n, dP.as<double>(), dI.as<int64_t>(), d_rec, c.stream,
-                      &launches);
-  } else {
-    rc = gibbs_device(trees, ndens, Np, Niter, add_entropy, dimmask, nullptr, 0, nullptr, 0, seed, s0, s1,
-                      dP.as<double>(), dI.as<int64_t>(), d_rec, c.stream, &launches);
-  }
+  // in-process multi-GPU: contiguous sample blocks, one per device; every device copies its shard straight into the
+  // caller's buffers (chains are addressed by global sample index => the result does not depend on the split)
+  const int G = gpus_for(n, 2048);
+  std::vector<double> ms(G, 0.0);
+  std::vector<int> nl(G, 0);
+  int rc = for_each_gpu(G, [&](int g) {
+    int64_t a, b;
+    shard_range(n, g, G, a, b);
+    a += s0;
+    b += s0;
+    return gibbs_host_block(trees, ndens, Np, Niter, add_entropy, dimmask, randU, randN, seed, a, b, L, perU, perN,
+                            points_out + (a - s0) * d, indices_out + (a - s0) * ndens,
+                            level_labels_out ? level_labels_out + (a - s0) * ndens * L : nullptr, &ms[g], &nl[g]);
+  });
   if (rc) return rc;
-  tm.stop();
-  c.last_launches = launches;
-  KDE_CUDA(cudaMemcpyAsync(points_out, dP.p, sizeof(double) * d * n, cudaMemcpyDeviceToHost, c.stream));
-  KDE_CUDA(cudaMemcpyAsync(indices_out, dI.p, sizeof(int64_t) * ndens * n, cudaMemcpyDeviceToHost, c.stream));
-  if (level_labels_out)
-    KDE_CUDA(cudaMemcpyAsync(level_labels_out, dR.p, sizeof(int64_t) * ndens * n * L, cudaMemcpyDeviceToHost, c.stream));
-  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  publish_timing(ms, nl);
   return 0;
 }
 
@@ -237,25 +377,27 @@ int kdeb200_eval(kdeb200_tree_t bd, const double *pos, int64_t M, int loo, int p
   if (!bd || !p_out) KDE_FAIL(2, "eval: NULL argument");
   if (!loo && !pos && M > 0) KDE_FAIL(2, "eval: pos is NULL");
   if (precision != KDEB200_F64 && precision != KDEB200_F32) KDE_FAIL(3, "eval: unknown precision %d", precision);
-  Context &c = ctx();
   if (loo) M = bd->N;
   if (M <= 0) return 0;
-  DevBuf dQ(c.stream), dO(c.stream);
-  if (!loo) {
-    KDE_CUDA(dQ.alloc(sizeof(double) * bd->d * M));
-    KDE_CUDA(cudaMemcpyAsync(dQ.p, pos, sizeof(double) * bd->d * M, cudaMemcpyHostToDevice, c.stream));
-  }
-  KDE_CUDA(dO.alloc(sizeof(double) * M));
-  Timer tm(c);
-  int launches = 0;
-  int rc = (precision == KDEB200_F64)
-               ? eval_device(bd, dQ.as<double>(), M, loo, 0, true, nullptr, dO.as<double>(), c.stream, &launches)
-               : eval_device_f32(bd, dQ.as<double>(), M, loo, dO.as<double>(), c.stream, &launches);
+  // in-process multi-GPU: query rows block-partitioned.  LOO rows are leaf rows: each device returns its block in leaf
+  // order and the host scatters through the permutation.  (FP32 LOO has no row-range form: one device.)
+  const bool f32_loo = loo && precision == KDEB200_F32;
+  const int G = f32_loo ? 1 : gpus_for(M, 4096);
+  std::vector<double> ms(G, 0.0);
+  std::vector<int> nl(G, 0);
+  std::vector<double> rows;
+  const bool scatter_on_host = loo && G > 1;
+  if (scatter_on_host) rows.resize(M);
+  int rc = for_each_gpu(G, [&](int g) {
+    int64_t a, b;
+    shard_range(M, g, G, a, b);
+    return eval_host_block(bd, pos, a, b, loo, precision, /*scatter=*/!scatter_on_host,
+                           scatter_on_host ? rows.data() + a : (loo ? p_out : p_out + a), &ms[g], &nl[g]);
+  });
   if (rc) return rc;
-  tm.stop();
-  c.last_launches = launches;
-  KDE_CUDA(cudaMemcpyAsync(p_out, dO.p, sizeof(double) * M, cudaMemcpyDeviceToHost, c.stream));
-  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  if (scatter_on_host)
+    for (int64_t j = 0; j < M; ++j) p_out[bd->h_perm[j]] = rows[j];
+  publish_timing(ms, nl);
   return 0;
 }
 
@@ -265,30 +407,34 @@ int kdeb200_loo_partial(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int
   if (int rc = ensure_init()) return rc;
   if (!bd || !sum_out || !zero_flag_out) KDE_FAIL(2, "loo_partial: NULL argument");
   if (j0 < 0 || j1 > bd->N || j0 > j1) KDE_FAIL(3, "loo_partial: bad row range");
-  Context &c = ctx();
-  *sum_out = 0.0;
-  *zero_flag_out = 0;
-  if (j0 == j1) return 0;
-  DevBuf dS(c.stream), dF(c.stream);
-  KDE_CUDA(dS.alloc(sizeof(double)));
-  KDE_CUDA(dF.alloc(sizeof(int)));
-  Timer tm(c);
-  int launches = 0;
-  if (int rc = loo_partial_device(bd, bw_var, j0, j1, dS.as<double>(), dF.as<int>(), c.stream, &launches)) return rc;
-  tm.stop();
-  c.last_launches = launches;
-  KDE_CUDA(cudaMemcpyAsync(sum_out, dS.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-  KDE_CUDA(cudaMemcpyAsync(zero_flag_out, dF.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  double ms = 0.0;
+  int nl = 0;
+  ScopedDevice sd(0);
+  if (int rc = loo_partial_block(bd, bw_var, j0, j1, sum_out, zero_flag_out, &ms, &nl)) return rc;
   return 0;
 }
 
 int kdeb200_loo_entropy(kdeb200_tree_t bd, const double *bw_var, double *H_out) {
   KDE_SERIALISE();
+  if (int rc = ensure_init()) return rc;
   if (!bd || !H_out) KDE_FAIL(2, "loo_entropy: NULL argument");
+  // in-process multi-GPU: leaf rows block-partitioned, partial sums added in block order
+  const int G = gpus_for(bd->N, 8192);
+  std::vector<double> sums(G, 0.0), ms(G, 0.0);
+  std::vector<int> flags(G, 0), nl(G, 0);
+  int rc = for_each_gpu(G, [&](int g) {
+    int64_t a, b;
+    shard_range(bd->N, g, G, a, b);
+    return loo_partial_block(bd, bw_var, a, b, &sums[g], &flags[g], &ms[g], &nl[g]);
+  });
+  if (rc) return rc;
   double s = 0.0;
   int flag = 0;
-  if (int rc = kdeb200_loo_partial(bd, bw_var, 0, bd->N, &s, &flag)) return rc;
+  for (int g = 0; g < G; ++g) {
+    s += sums[g];
+    flag |= flags[g];
+  }
+  publish_timing(ms, nl);
   // evalAvgLogL returns -Inf under the zero rule; entropy = -evalAvgLogL
   *H_out = flag ? std::numeric_limits<double>::infinity() : -s;
   return 0;
@@ -300,11 +446,32 @@ int kdeb200_kde_lcv(int d, int64_t N, const double *points, double *bw_std_out, 
   return kde_lcv(d, N, points, 0, N, nullptr, nullptr, bw_std_out, nloo_calls_out);
 }
 
+int kdeb200_kde_lcv_sharded_v(int d, int64_t N, const double *points, int64_t j0, int64_t j1,
+                              kdeb200_allreduce_v_fn allreduce, void *user, double *bw_std_out, int *nloo_calls_out) {
+  KDE_SERIALISE();
+  if (!points || !bw_std_out || !allreduce) KDE_FAIL(2, "kde_lcv_sharded: NULL argument");
+  return kde_lcv(d, N, points, j0, j1, allreduce, user, bw_std_out, nloo_calls_out);
+}
+
+namespace {
+struct ScalarExchange {  // the scalar callback form on top of the vector exchange: one call per entry
+  kdeb200_allreduce_fn fn;
+  void *user;
+};
+int scalar_exchange_adapter(double *sums, int *flags, int count, void *user) {
+  ScalarExchange *x = static_cast<ScalarExchange *>(user);
+  for (int i = 0; i < count; ++i)
+    if (int r = x->fn(&sums[i], &flags[i], x->user)) return r;
+  return 0;
+}
+}  // namespace
+
 int kdeb200_kde_lcv_sharded(int d, int64_t N, const double *points, int64_t j0, int64_t j1,
                             kdeb200_allreduce_fn allreduce, void *user, double *bw_std_out, int *nloo_calls_out) {
   KDE_SERIALISE();
   if (!points || !bw_std_out || !allreduce) KDE_FAIL(2, "kde_lcv_sharded: NULL argument");
-  return kde_lcv(d, N, points, j0, j1, allreduce, user, bw_std_out, nloo_calls_out);
+  ScalarExchange x{allreduce, user};
+  return kde_lcv(d, N, points, j0, j1, scalar_exchange_adapter, &x, bw_std_out, nloo_calls_out);
 }
 
 int kdeb200_pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms) {

@@ -101,46 +101,56 @@ static int init_device(int device) {
   return make_context(c, device, 0);
 }
 
+// devices[0] becomes (or must already be) the primary; the others follow in the given order.  Repeating a device is
+// allowed: several contexts (streams, host threads, tree replicas) then share one GPU -- no speed-up, but the whole
+// sharding path can be exercised on a single-GPU box (tests) and small GPUs can be oversubscribed deliberately.
+static int init_multi_devices(const int *devices, int n) {
+  int count = 0;
+  KDE_CUDA(cudaGetDeviceCount(&count));
+  if (count <= 0) KDE_FAIL(20, "no CUDA device visible: libkdeb200 has no CPU fallback");
+  if (n < 1 || n > KDEB200_MAX_GPUS) KDE_FAIL(21, "kdeb200_init_multi: between 1 and %d GPUs (got %d)", KDEB200_MAX_GPUS, n);
+  for (int i = 0; i < n; ++i)
+    if (devices[i] < 0 || devices[i] >= count)
+      KDE_FAIL(21, "kdeb200_init_multi: device %d out of range (0..%d)", devices[i], count - 1);
+  if (int rc = init_device(devices[0])) return rc;  // no-op when already bound there; otherwise a full re-bind
+  for (int s = g_nctx - 1; s >= 1; --s) drop_context(g_ctx[s]);
+  g_nctx = 1;
+  for (int i = 1; i < n; ++i) {
+    if (int rc = make_context(g_ctx[i], devices[i], i)) {
+      for (int s = i; s >= 1; --s) drop_context(g_ctx[s]);
+      cudaSetDevice(g_ctx[0].device);
+      return rc;
+    }
+    g_nctx = i + 1;
+  }
+  for (int a = 0; a < g_nctx; ++a)  // peer access for the tree replication copies (ignored where unsupported)
+    for (int b = 0; b < g_nctx; ++b) {
+      if (g_ctx[a].device == g_ctx[b].device) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, g_ctx[a].device, g_ctx[b].device);
+      if (can) {
+        cudaSetDevice(g_ctx[a].device);
+        if (cudaDeviceEnablePeerAccess(g_ctx[b].device, 0) != cudaSuccess) cudaGetLastError();  // already enabled
+      }
+    }
+  KDE_CUDA(cudaSetDevice(g_ctx[0].device));
+  return 0;
+}
+
 // The primary plus the next visible devices (in index order) until `ngpus` contexts exist; ngpus <= 0: every visible device.
 static int init_multi(int ngpus) {
   int count = 0;
   KDE_CUDA(cudaGetDeviceCount(&count));
   if (count <= 0) KDE_FAIL(20, "no CUDA device visible: libkdeb200 has no CPU fallback");
-  if (ngpus <= 0) ngpus = count;
+  if (ngpus <= 0) ngpus = count < KDEB200_MAX_GPUS ? count : KDEB200_MAX_GPUS;
   if (ngpus > count) KDE_FAIL(21, "kdeb200_init_multi: %d GPUs requested, %d visible", ngpus, count);
-  if (ngpus > KDEB200_MAX_GPUS) KDE_FAIL(21, "kdeb200_init_multi: at most %d GPUs", KDEB200_MAX_GPUS);
-  if (!g_ctx[0].ready) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
-    if (int rc = init_device(dev)) return rc;
-  }
-  for (int s = g_nctx - 1; s >= ngpus; --s) drop_context(g_ctx[s]);  // shrinking
-  if (g_nctx > ngpus) g_nctx = ngpus;
-  int dev = 0;
-  std::vector<char> used(count, 0);
-  for (int s = 0; s < g_nctx; ++s) used[g_ctx[s].device] = 1;
-  while (g_nctx < ngpus) {
-    while (dev < count && used[dev]) ++dev;
-    if (int rc = make_context(g_ctx[g_nctx], dev, g_nctx)) {
-      cudaSetDevice(g_ctx[0].device);
-      return rc;
-    }
-    used[dev] = 1;
-    ++g_nctx;
-  }
-  for (int a = 0; a < g_nctx; ++a)  // peer access for the tree replication copies (ignored where unsupported)
-    for (int b = 0; b < g_nctx; ++b) {
-      if (a == b) continue;
-      int can = 0;
-      cudaDeviceCanAccessPeer(&can, g_ctx[a].device, g_ctx[b].device);
-      if (can) {
-        cudaSetDevice(g_ctx[a].device);
-        cudaError_t e = cudaDeviceEnablePeerAccess(g_ctx[b].device, 0);
-        if (e != cudaSuccess) cudaGetLastError();  // already enabled
-      }
-    }
-  KDE_CUDA(cudaSetDevice(g_ctx[0].device));
-  return 0;
+  int primary = 0;
+  if (g_ctx[0].ready) primary = g_ctx[0].device;
+  else if (cudaGetDevice(&primary) != cudaSuccess) primary = 0;
+  std::vector<int> devs{primary};
+  for (int dev = 0; dev < count && (int)devs.size() < ngpus; ++dev)
+    if (dev != primary) devs.push_back(dev);
+  return init_multi_devices(devs.data(), (int)devs.size());
 }
 
 int ensure_init() {
@@ -182,6 +192,12 @@ int kdeb200_init(int device) {
 int kdeb200_init_multi(int ngpus) {
   std::lock_guard<std::mutex> lk(g_mu);
   return init_multi(ngpus);
+}
+
+int kdeb200_init_multi_devices(const int *devices, int n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!devices) KDE_FAIL(2, "init_multi_devices: NULL");
+  return init_multi_devices(devices, n);
 }
 
 int kdeb200_multi_count(int *ngpus) {

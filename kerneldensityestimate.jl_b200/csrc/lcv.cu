@@ -30,6 +30,7 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
                 const int64_t *left, const int64_t *right, const int64_t *perm, bool gibbs_records,
                 kdeb200_tree_t *out);
 int tree_destroy(kdeb200_tree_t t);
+int tree_on(kdeb200_tree_t t, int slot, kdeb200_tree_t *out);
 int loo_partial_device(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int64_t j1, double *d_sum, int *d_flag,
                        cudaStream_t st, int *launches);
 
@@ -190,7 +191,7 @@ struct Golden {
 // j0, j1 and allreduce: this process owns the leaf rows [j0, j1) of every nLOO_LL evaluation and the callback sums the
 // partial likelihood (and ORs the zero flag) over the processes -- the multi-GPU split of SURVEY.md 8e.  allreduce ==
 // nullptr: single process, all rows.  Small N runs the fused kernel redundantly on every process (no exchange needed).
-int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb200_allreduce_fn allreduce,
+int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb200_allreduce_v_fn allreduce,
             void *user, double *bw_std_out, int *ncalls_out) {
   if (int rc = ensure_init()) return rc;
   if (d < 1) KDE_FAIL(3, "kde_lcv: d must be >= 1");
@@ -202,7 +203,7 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
   }
   if (j0 < 0 || j1 > N || j0 > j1) KDE_FAIL(3, "kde_lcv: bad row range [%lld,%lld) of %lld", (long long)j0, (long long)j1, (long long)N);
   Context &c = ctx();
-  const Golden G;
+  const Golden G_;
   const double tol = 1e-2;
 
   // kde!(points, [1.0]): weights ones(N) / N; marginal(): renormalised by their sequential sum
@@ -262,8 +263,8 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
     P.N = (int)N;
     P.norm0 = std::pow(2.0 * M_PI, 0.5);  // src/DualTree01.jl:325 with d = 1
     P.tol = tol;
-    P.Cg = G.Cg;
-    P.Rg = G.Rg;
+    P.Cg = G_.Cg;
+    P.Rg = G_.Rg;
     std::vector<double> out(3 * d);
     cudaError_t e = cudaMemcpyAsync(base, leaf.data(), b_leaf, cudaMemcpyHostToDevice, c.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(base + up(b_leaf), dims.data(), b_dims, cudaMemcpyHostToDevice, c.stream);
@@ -288,74 +289,175 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
     return 0;
   }
 
-  // large N: host golden loop, one tiled LOO launch sequence and one scalar back per step
-  double *d_sum = nullptr;
-  int *d_flag = nullptr;
-  KDE_CUDA(cudaMallocAsync(&d_sum, 256, c.stream));
-  d_flag = reinterpret_cast<int *>(d_sum + 8);
+  // Large N: the d golden-section searches are independent, so they advance in LOCK-STEP: every step queues the tiled
+  // LOO launches of all unfinished dimensions back to back -- on every GPU of the in-process set, each owning a block
+  // of this process's leaf rows -- then ONE synchronisation per GPU brings the partial likelihoods back (and, between
+  // processes, ONE vector all-reduce).  ~20 round trips instead of ~20 d, and d times more work in flight per step.
+  struct Search {  // golden (src/CrossValidation.jl:44-98) as a state machine: next() -> alpha to evaluate, feed(H)
+    double x0, x1, x2, x3, f1 = 0, f2 = 0, Cg, Rg, tol;
+    int phase = 0, ncalls = 0;  // 0: f1 pending, 1: f2 pending, 2: loop
+    bool want_f2 = false, done = false;
+    double pending() const { return (phase == 0) ? x1 : (phase == 1 ? x2 : (want_f2 ? x2 : x1)); }
+    void advance() {  // decide the next evaluation of the loop, or finish
+      if (!(std::fabs(x3 - x0) > tol * (std::fabs(x1) + std::fabs(x2))) || ncalls > 4096) {
+        done = true;
+        return;
+      }
+      if (f2 < f1) {
+        x0 = x1;
+        x1 = x2;
+        x2 = Rg * x1 + Cg * x3;
+        f1 = f2;
+        want_f2 = true;
+      } else {
+        x3 = x2;
+        x2 = x1;
+        x1 = Rg * x2 + Cg * x0;
+        f2 = f1;
+        want_f2 = false;
+      }
+    }
+    void feed(double H) {
+      ++ncalls;
+      if (phase == 0) {
+        f1 = H;
+        phase = 1;
+      } else if (phase == 1) {
+        f2 = H;
+        phase = 2;
+        advance();
+      } else {
+        if (want_f2) f2 = H; else f1 = H;
+        advance();
+      }
+    }
+    double xmin() const { return (f1 < f2) ? x1 : x2; }
+  };
+  const int G = (j1 - j0 >= 8192 * (int64_t)multi_count()) ? multi_count() : 1;
+  std::vector<kdeb200_tree_t> trees(d, nullptr);
+  std::vector<Search> S(d);
+  std::vector<double> b(d);
   int rc = 0, launches = 0;
   for (int k = 0; k < d && rc == 0; ++k) {
     Marginal &m = margs[k];
     const double h = (m.minm + m.maxm) / 2.0;
-    double b = h * h;
-    std::vector<double> bandwidth(2 * N, b);
-    kdeb200_tree_t t = nullptr;
-    rc = tree_create(1, N, m.means.data(), bandwidth.data(), m.weights.data(), nullptr, nullptr, m.perm.data(), false, &t);
-    if (rc) break;
-    int ncalls = 0;
-    auto nloo = [&](double alpha, double &H) -> int {
-      const double a2 = alpha * alpha;
-      b = b * a2;
-      double hs[9] = {0};
-      if (j1 > j0) {
-        if (int r = loo_partial_device(t, &b, j0, j1, d_sum, d_flag, c.stream, &launches)) return r;
-        KDE_CUDA(cudaMemcpyAsync(hs, d_sum, sizeof(hs), cudaMemcpyDeviceToHost, c.stream));
-        KDE_CUDA(cudaStreamSynchronize(c.stream));
-      }
-      int flag;
-      std::memcpy(&flag, &hs[8], sizeof(int));
-      if (allreduce) {
-        if (int r = allreduce(&hs[0], &flag, user)) KDE_FAIL(9, "kde_lcv: the all-reduce callback failed (%d)", r);
-      }
-      H = flag ? std::numeric_limits<double>::infinity() : -hs[0];
-      b = b / a2;
-      ++ncalls;
-      return 0;
-    };
+    b[k] = h * h;
+    std::vector<double> bandwidth(2 * N, b[k]);
+    rc = tree_create(1, N, m.means.data(), bandwidth.data(), m.weights.data(), nullptr, nullptr, m.perm.data(), false, &trees[k]);
     const double ax = 2.0 * m.minm / (m.minm + m.maxm), bx = 1.0, cx = 2.0 * m.maxm / (m.minm + m.maxm);
-    double x0 = ax, x3 = cx, x1, x2, f1 = 0, f2 = 0;
+    Search &s = S[k];
+    s.Cg = G_.Cg; s.Rg = G_.Rg; s.tol = tol;
+    s.x0 = ax; s.x3 = cx;
     if (std::fabs(cx - bx) > std::fabs(bx - ax)) {
-      x1 = bx;
-      x2 = bx + G.Cg * (cx - bx);
+      s.x1 = bx;
+      s.x2 = bx + G_.Cg * (cx - bx);
     } else {
-      x1 = bx - G.Cg * (bx - ax);
-      x2 = bx;
+      s.x1 = bx - G_.Cg * (bx - ax);
+      s.x2 = bx;
     }
-    rc = nloo(x1, f1);
-    if (!rc) rc = nloo(x2, f2);
-    while (!rc && std::fabs(x3 - x0) > tol * (std::fabs(x1) + std::fabs(x2)) && ncalls <= 4096) {
-      if (f2 < f1) {
-        x0 = x1;
-        x1 = x2;
-        x2 = G.Rg * x1 + G.Cg * x3;
-        f1 = f2;
-        rc = nloo(x2, f2);
-      } else {
-        x3 = x2;
-        x2 = x1;
-        x1 = G.Rg * x2 + G.Cg * x0;
-        f2 = f1;
-        rc = nloo(x1, f1);
+  }
+  // per GPU: result slots [d] of (sum, flag) in one small device buffer, replicas of the d trees
+  struct PerGpu {
+    double *d_res = nullptr;  // d x 2 doubles: sum, flag (int in the low word)
+    std::vector<kdeb200_tree_t> t;
+    std::vector<double> h_res;
+    int64_t r0 = 0, r1 = 0;
+  };
+  std::vector<PerGpu> gp(G);
+  for (int g = 0; g < G && rc == 0; ++g) {
+    ScopedDevice sd(g);
+    Context &cg = ctx();
+    const int64_t n = j1 - j0, base = n / G, rem = n % G;
+    gp[g].r0 = j0 + g * base + (g < rem ? g : rem);
+    gp[g].r1 = gp[g].r0 + base + (g < rem ? 1 : 0);
+    gp[g].t.assign(d, nullptr);
+    gp[g].h_res.assign(2 * d, 0.0);
+    cudaError_t e = cudaMallocAsync(&gp[g].d_res, sizeof(double) * 2 * d, cg.stream);
+    if (e != cudaSuccess) {
+      set_error("kde_lcv: cudaMallocAsync: %s", cudaGetErrorString(e));
+      rc = 100 + (int)e;
+    }
+    for (int k = 0; k < d && rc == 0; ++k) rc = tree_on(trees[k], g, &gp[g].t[k]);
+  }
+  std::vector<int> active;
+  std::vector<double> sums(d);
+  std::vector<int> flags(d);
+  while (rc == 0) {
+    active.clear();
+    for (int k = 0; k < d; ++k)
+      if (!S[k].done) active.push_back(k);
+    if (active.empty()) break;
+    std::vector<double> a2(d, 1.0);
+    for (int k : active) {
+      const double alpha = S[k].pending();
+      a2[k] = alpha * alpha;  // src/CrossValidation.jl:17
+      b[k] = b[k] * a2[k];    // updateBandwidth!(bd, bd.bandwidth * alpha)
+    }
+    for (int g = 0; g < G && rc == 0; ++g) {  // queue everything, no host wait in between
+      ScopedDevice sd(g);
+      Context &cg = ctx();
+      if (gp[g].r1 > gp[g].r0) {
+        for (int k : active) {
+          rc = loo_partial_device(gp[g].t[k], &b[k], gp[g].r0, gp[g].r1, gp[g].d_res + 2 * k,
+                                  reinterpret_cast<int *>(gp[g].d_res + 2 * k + 1), cg.stream, &launches);
+          if (rc) break;
+        }
       }
     }
-    tree_destroy(t);
+    for (int g = 0; g < G && rc == 0; ++g) {  // only now wait: a pageable D2H blocks the host until the stream drains
+      ScopedDevice sd(g);
+      if (gp[g].r1 <= gp[g].r0) continue;
+      cudaError_t e = cudaMemcpyAsync(gp[g].h_res.data(), gp[g].d_res, sizeof(double) * 2 * d, cudaMemcpyDeviceToHost, ctx().stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+      if (e != cudaSuccess) {
+        set_error("kde_lcv: LOO kernels on GPU slot %d: %s", g, cudaGetErrorString(e));
+        rc = 100 + (int)e;
+      }
+    }
     if (rc) break;
-    finish(k, (f1 < f2) ? x1 : x2);
-    if (ncalls_out) ncalls_out[k] = ncalls;
+    int na = 0;
+    for (int k : active) {  // partial sums of the row blocks in block order
+      double sum = 0.0;
+      int flag = 0;
+      for (int g = 0; g < G; ++g)
+        if (gp[g].r1 > gp[g].r0) {
+          sum += gp[g].h_res[2 * k];
+          int f;
+          std::memcpy(&f, &gp[g].h_res[2 * k + 1], sizeof(int));
+          flag |= f;
+        }
+      sums[na] = sum;
+      flags[na] = flag;
+      ++na;
+    }
+    if (allreduce) {
+      if (int r = allreduce(sums.data(), flags.data(), na, user)) {
+        set_error("kde_lcv: the all-reduce callback failed (%d)", r);
+        rc = 9;
+        break;
+      }
+    }
+    na = 0;
+    for (int k : active) {
+      const double H = flags[na] ? std::numeric_limits<double>::infinity() : -sums[na];
+      ++na;
+      b[k] = b[k] / a2[k];  // updateBandwidth!(bd, bd.bandwidth / alpha): the ulp drift is part of the reference
+      S[k].feed(H);
+    }
   }
-  cudaFreeAsync(d_sum, c.stream);
-  c.last_launches = launches;
-  return rc;
+  for (int g = 0; g < G; ++g) {
+    ScopedDevice sd(g);
+    if (gp[g].d_res) cudaFreeAsync(gp[g].d_res, ctx().stream);
+  }
+  for (int k = 0; k < d; ++k)
+    if (trees[k]) tree_destroy(trees[k]);
+  if (rc) return rc;
+  for (int k = 0; k < d; ++k) {
+    finish(k, S[k].xmin());
+    if (ncalls_out) ncalls_out[k] = S[k].ncalls;
+  }
+  ctx_at(0).last_launches = launches;
+  return 0;
 }
 
 }  // namespace kdeb200

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <limits>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "tree.cuh"
@@ -372,7 +373,53 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
   if ((e = cudaMemcpyAsync(t->d_perm, pr.data(), sizeof(int64_t) * pr.size(), cudaMemcpyHostToDevice, c.stream)) != cudaSuccess) return fail(e, "H2D perm");
   if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return fail(e, "sync");  // host vectors die here
   t->device_bytes = total;
+  t->slot = c.slot;
+  t->h_perm = std::move(pr);
   *out = t;
+  return 0;
+}
+
+// Replica of a tree on another GPU of the in-process set: ONE peer copy of the single allocation (NVLink when peer
+// access is on, staged by the driver otherwise), every pointer rebased.  Created on first use, freed with the tree.
+int tree_on(kdeb200_tree_t t, int slot, kdeb200_tree_t *out) {
+  if (!t) KDE_FAIL(2, "tree_on: NULL tree");
+  if (slot == t->slot) {
+    *out = t;
+    return 0;
+  }
+  if (t->slot != 0) KDE_FAIL(3, "tree_on: only trees created on the primary device can be replicated");
+  if (slot < 0 || slot >= multi_count()) KDE_FAIL(3, "tree_on: slot %d outside the multi-GPU set", slot);
+  if (t->replica[slot]) {
+    *out = t->replica[slot];
+    return 0;
+  }
+  Context &src = ctx_at(0);
+  Context &dst = ctx_at(slot);
+  ScopedDevice sd(slot);
+  char *base = nullptr;
+  KDE_CUDA(cudaMallocAsync(&base, t->device_bytes, dst.stream));
+  cudaError_t e = cudaMemcpyPeerAsync(base, dst.device, t->d_base, src.device, t->device_bytes, dst.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(dst.stream);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(base, dst.stream);
+    KDE_FAIL(100 + (int)e, "tree_on: peer copy to device %d: %s", dst.device, cudaGetErrorString(e));
+  }
+  kdeb200_tree_s *r = new kdeb200_tree_s(*t);
+  for (auto &p : r->replica) p = nullptr;
+  const ptrdiff_t off = base - t->d_base;
+  auto rebase = [&](auto *&p) {
+    if (p) p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(reinterpret_cast<char *>(p) + off);
+  };
+  r->d_base = base;
+  rebase(r->d_buf);
+  rebase(r->d_labels);
+  rebase(r->d_levperm);
+  rebase(r->d_leaf);
+  rebase(r->d_perm);
+  r->d_leaf32 = nullptr;
+  r->slot = slot;
+  t->replica[slot] = r;
+  *out = r;
   return 0;
 }
 
@@ -388,6 +435,16 @@ int tree_destroy(kdeb200_tree_t t) {
   const double t1 = now();
   if (t->d_base) cudaFreeAsync(t->d_base, c.stream);
   if (t->d_leaf32) cudaFreeAsync(t->d_leaf32, c.stream);
+  for (int s = 1; s < KDEB200_MAX_GPUS; ++s)
+    if (kdeb200_tree_s *r = t->replica[s]) {
+      if (s < multi_count() && ctx_at(s).ready) {  // the context may be gone after a re-init: its memory went with it
+        ScopedDevice sd(s);
+        cudaDeviceSynchronize();
+        if (r->d_base) cudaFreeAsync(r->d_base, ctx_at(s).stream);
+        if (r->d_leaf32) cudaFreeAsync(r->d_leaf32, ctx_at(s).stream);
+      }
+      delete r;
+    }
   const double t2 = now();
   delete t;
   if (trace) fprintf(stderr, "[kdeb200] tree_destroy: sync %.3f ms, free %.3f ms, delete %.3f ms\n", t1 - t0, t2 - t1, now() - t2);

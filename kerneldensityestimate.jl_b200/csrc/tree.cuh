@@ -41,4 +41,12 @@ struct kdeb200_tree_s {
   int64_t *d_perm = nullptr;    // leaf order: original 0-based index
   float *d_leaf32 = nullptr;    // lazily built FP32 shadow of d_leaf (centred, pre-scaled), eval_f32.cu
   size_t device_bytes = 0;
+  int slot = 0;                 // context slot that owns the device memory (0 = primary)
+  std::vector<int64_t> h_perm;  // host copy of d_perm (scatter of sharded LOO rows)
+  kdeb200_tree_s *replica[KDEB200_MAX_GPUS] = {nullptr};  // copies on the other GPUs of the in-process set (lazy)
 };
+
+namespace kdeb200 {
+// the tree's records on the GPU of context `slot` (the handle itself for slot 0; otherwise a lazily made peer copy)
+int tree_on(kdeb200_tree_t t, int slot, kdeb200_tree_t *out);
+}

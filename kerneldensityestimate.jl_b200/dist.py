@@ -173,23 +173,26 @@ def kde_sharded(points, group=None, device=None, loo_factory=None):
         dev = _exchange_device(device, group) if world > 1 else None
         failure = []
 
-        def exchange(psum, pflag, _user):
+        def exchange(psum, pflag, count, _user):
+            # the d golden-section searches run in lock-step: ONE all-reduce per step carries the `count` partial
+            # likelihoods and zero flags of that step (flags ride along as doubles; sum > 0 <=> some rank flagged)
             try:
                 if world > 1:
-                    ts = torch.tensor([psum[0]], dtype=torch.float64, device=dev)
-                    tf = torch.tensor([pflag[0]], dtype=torch.int32, device=dev)
-                    dist.all_reduce(ts, op=dist.ReduceOp.SUM, group=group)
-                    dist.all_reduce(tf, op=dist.ReduceOp.MAX, group=group)
-                    psum[0], pflag[0] = float(ts.item()), int(tf.item())
+                    buf = [psum[i] for i in range(count)] + [float(pflag[i]) for i in range(count)]
+                    t = torch.tensor(buf, dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                    v = t.tolist()
+                    for i in range(count):
+                        psum[i], pflag[i] = v[i], int(v[count + i] > 0.0)
                 return 0
             except Exception as e:  # exceptions must not unwind through the C frames
                 failure.append(e)
                 return 1
-        cb = _lib.allreduce_fn(exchange)
+        cb = _lib.allreduce_v_fn(exchange)
         a, b = shard_range(N, rank, world)
         flat = np.ascontiguousarray(pts.T).ravel()
         bw = np.zeros(d)
-        rc = _lib.lib().kdeb200_kde_lcv_sharded(d, N, _lib.fptr(flat), a, b, cb, None, _lib.fptr(bw), None)
+        rc = _lib.lib().kdeb200_kde_lcv_sharded_v(d, N, _lib.fptr(flat), a, b, cb, None, _lib.fptr(bw), None)
         if failure:
             raise failure[0]
         _lib.check(rc)
