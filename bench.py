@@ -304,7 +304,8 @@ def secondary_sharded(K, kd, torch, dist, rank, world, dev, args):
     # content check: the first 1024 densities of the NEXT rank's block, recomputed here
     fa, _ = kd.shard_range(n, (rank + 1) % world, world)
     chk = K.evaluateDualTree(p, pos[:, fa:fa + 1024])
-    ok = torch.tensor([int(np.array_equal(chk, g_out[fa:fa + 1024].cpu().numpy()))], device=dev)
+    got = g_out[fa:fa + 1024].cpu().numpy()  # rows are independent; the component-split count differs with the block size
+    ok = torch.tensor([int(bool(np.max(np.abs(chk - got) / chk) < 1e-13))], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     out["c5"] = {"workload": "C5: %d components x %d queries, 3-D, f64, queries sharded over %d GPUs + NCCL all-gather" % (n, n, world),
                  "value": float(n) * n / (float(t.item()) * 1e-3), "unit": "evals/s", "ms_per_call": float(t.item()),
