@@ -43,9 +43,13 @@ ScopedDevice::~ScopedDevice() {
 
 static std::mutex g_mu;
 
+void gibbs_drop_schedules(int slot);  // gibbs.cu
+
 static void drop_context(Context &c) {
   if (!c.ready) return;
   cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  gibbs_drop_schedules(c.slot);
   cudaStreamSynchronize(c.stream);
   cudaFree(c.d_exptab);
   cudaEventDestroy(c.ev0);

@@ -1,7 +1,10 @@
 // gibbs.cu -- host side of K1: schedule construction, launch, Philox stream materialisation.
 // The kernel lives in gibbs_kernel.cuh and is instantiated once per dimension in gibbs_d<N>.cu.
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <list>
+#include <mutex>
 #include <vector>
 
 #include "gibbs_kernel.cuh"
@@ -122,6 +125,113 @@ int gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels,
   return 0;
 }
 
+// ---- schedule cache -----------------------------------------------------------------------------------------
+// The static schedule (draws + tile list) depends only on the tree set, Niter and the mask class.  It used to be rebuilt,
+// allocated (3 x cudaMallocAsync), uploaded and SYNCHRONISED on every call -- irrelevant at 1M samples, but it was the
+// difference between a 0.34 ms kernel and a 0.39 ms call at the small configurations, and it made kdeb200_gibbs_device
+// block.  Entries are keyed by (context slot, tree handles, Niter, masked) and invalidated wholesale whenever any tree
+// is destroyed (a global epoch); each context keeps the 8 most recent.  Batch counters come from a ring of 256 slots
+// per entry, zeroed once at creation and reset by the LAST CTA of each launch.
+std::atomic<uint64_t> g_tree_epoch{1};
+void gibbs_invalidate_schedules() { g_tree_epoch.fetch_add(1); }
+
+namespace {
+struct SchedEntry {
+  uint64_t epoch = 0;
+  int slot = 0, M = 0, T = 0;
+  bool masked = false;
+  kdeb200_tree_t trees[KDEB200_MAX_DENS] = {nullptr};
+  char *d_base = nullptr;  // draws | tiles | counters, one allocation on the context's device
+  Draw *d_draws = nullptr;
+  TileDesc *d_tiles = nullptr;
+  int *d_counters = nullptr;
+  int ndraws = 0, ntiles = 0;
+  unsigned next_counter = 0;
+};
+constexpr int SCHED_COUNTERS = 256;
+constexpr size_t SCHED_KEEP = 8;
+std::mutex g_sched_mu;
+std::list<SchedEntry> g_sched[KDEB200_MAX_GPUS];
+
+void sched_free(SchedEntry &e, cudaStream_t st) {
+  if (e.d_base) cudaFreeAsync(e.d_base, st);
+  e.d_base = nullptr;
+}
+}  // namespace
+
+// drops every cached schedule of a context (its device memory is about to go away)
+void gibbs_drop_schedules(int slot) {
+  std::lock_guard<std::mutex> lk(g_sched_mu);
+  for (auto &e : g_sched[slot]) sched_free(e, ctx_at(slot).stream);
+  g_sched[slot].clear();
+}
+
+static int sched_get(const kdeb200_tree_t *trees, int M, int L, int T, bool masked, cudaStream_t st, SchedEntry *out,
+                     int **counter) {
+  Context &c = ctx();
+  std::lock_guard<std::mutex> lk(g_sched_mu);
+  auto &lst = g_sched[c.slot];
+  const uint64_t epoch = g_tree_epoch.load();
+  for (auto it = lst.begin(); it != lst.end();) {  // entries from before the last tree_destroy may point at freed records
+    if (it->epoch != epoch) {
+      sched_free(*it, c.stream);
+      it = lst.erase(it);
+    } else {
+      ++it;
+    }
+  }
+  for (auto it = lst.begin(); it != lst.end(); ++it) {
+    if (it->M != M || it->T != T || it->masked != masked) continue;
+    bool same = true;
+    for (int j = 0; j < M; ++j) same = same && it->trees[j] == trees[j];
+    if (!same) continue;
+    lst.splice(lst.begin(), lst, it);  // most recently used first
+    *counter = it->d_counters + (it->next_counter++ % SCHED_COUNTERS);
+    *out = *it;
+    return 0;
+  }
+  Schedule S;
+  build_schedule(trees, M, L, T, masked, S);
+  SchedEntry e;
+  e.epoch = epoch;
+  e.slot = c.slot;
+  e.M = M;
+  e.T = T;
+  e.masked = masked;
+  for (int j = 0; j < M; ++j) e.trees[j] = trees[j];
+  e.ndraws = (int)S.draws.size();
+  e.ntiles = (int)S.tiles.size();
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t b_draws = up(sizeof(Draw) * S.draws.size()), b_tiles = up(sizeof(TileDesc) * S.tiles.size()),
+               b_cnt = up(sizeof(int) * SCHED_COUNTERS);
+  // the upload runs on the library stream of this context and is complete before the entry is published; the caller's
+  // stream only ever sees finished buffers
+  KDE_CUDA(cudaMallocAsync(&e.d_base, b_draws + b_tiles + b_cnt, c.stream));
+  e.d_draws = reinterpret_cast<Draw *>(e.d_base);
+  e.d_tiles = reinterpret_cast<TileDesc *>(e.d_base + b_draws);
+  e.d_counters = reinterpret_cast<int *>(e.d_base + b_draws + b_tiles);
+  cudaError_t err = cudaMemcpyAsync(e.d_draws, S.draws.data(), sizeof(Draw) * S.draws.size(), cudaMemcpyHostToDevice, c.stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(e.d_tiles, S.tiles.data(), sizeof(TileDesc) * S.tiles.size(), cudaMemcpyHostToDevice, c.stream);
+  if (err == cudaSuccess) err = cudaMemsetAsync(e.d_counters, 0, b_cnt, c.stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(c.stream);  // S's vectors are pageable host memory
+  if (err != cudaSuccess) {
+    cudaFreeAsync(e.d_base, c.stream);
+    KDE_FAIL(100 + (int)err, "gibbs: uploading the schedule: %s", cudaGetErrorString(err));
+  }
+  (void)st;
+  lst.push_front(e);
+  while (lst.size() > SCHED_KEEP) {
+    // an evicted entry may still be read by a kernel in flight on a caller stream: release it only after the device
+    // has drained (rare: more than 8 distinct tree sets alternating)
+    cudaDeviceSynchronize();
+    sched_free(lst.back(), c.stream);
+    lst.pop_back();
+  }
+  *counter = lst.front().d_counters + (lst.front().next_counter++ % SCHED_COUNTERS);
+  *out = lst.front();
+  return 0;
+}
+
 int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
                  const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN, int64_t nN,
                  uint64_t seed, int64_t s0, int64_t s1, double *d_points, int64_t *d_indices,
@@ -138,9 +248,11 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
     if (s1 * perU > nU + 1) KDE_FAIL(7, "gibbs: randU too short (%lld < %lld)", (long long)nU, (long long)(s1 * perU - 1));
     if (s1 * perN > nN) KDE_FAIL(7, "gibbs: randN too short (%lld < %lld)", (long long)nN, (long long)(s1 * perN));
   }
-  for (int j = 0; j < ndens; ++j)
+  for (int j = 0; j < ndens; ++j) {
     if (trees[j]->degenerate)
-      KDE_FAIL(8, "gibbs: density %d has a non-positive or non-finite bandwidth/mean; not supported on the GPU path (no CPU fallback)", j + 1);
+      KDE_FAIL(8, "gibbs: density %d has a non-positive, non-finite or out-of-range (variance outside [1e-30, 1e30]) bandwidth/mean; not supported on the GPU path (no CPU fallback)", j + 1);
+    if (trees[j]->slot != c.slot) KDE_FAIL(3, "gibbs: tree %d lives on another GPU of the set than the calling context", j);
+  }
 
   GibbsParams P;
   std::memset(&P, 0, sizeof(P));
@@ -157,22 +269,12 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
         if (i != j && P.mask[i][k]) o = 1;
       P.other[j][k] = o;
     }
-  Schedule S;
-  build_schedule(trees, ndens, L, Niter, masked, S);
-
-  Draw *d_draws = nullptr;
-  TileDesc *d_tiles = nullptr;
+  SchedEntry E;
   int *d_counter = nullptr;
-  KDE_CUDA(cudaMallocAsync(&d_draws, sizeof(Draw) * S.draws.size(), st));
-  KDE_CUDA(cudaMallocAsync(&d_tiles, sizeof(TileDesc) * S.tiles.size(), st));
-  KDE_CUDA(cudaMallocAsync(&d_counter, 256, st));
-  KDE_CUDA(cudaMemsetAsync(d_counter, 0, 256, st));
-  KDE_CUDA(cudaMemcpyAsync(d_draws, S.draws.data(), sizeof(Draw) * S.draws.size(), cudaMemcpyHostToDevice, st));
-  KDE_CUDA(cudaMemcpyAsync(d_tiles, S.tiles.data(), sizeof(TileDesc) * S.tiles.size(), cudaMemcpyHostToDevice, st));
-  KDE_CUDA(cudaStreamSynchronize(st));  // S's vectors are pageable host memory
+  if (int rc = sched_get(trees, ndens, L, Niter, masked, st, &E, &d_counter)) return rc;
 
-  P.draws = d_draws;
-  P.tiles = d_tiles;
+  P.draws = E.d_draws;
+  P.tiles = E.d_tiles;
   P.counter = d_counter;
   P.exptab = c.d_exptab;
   P.ec = make_exp_consts();
@@ -186,8 +288,8 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
   P.perU = perU;
   P.perN = perN;
   P.seed = seed;
-  P.ndraws = (int)S.draws.size();
-  P.ntiles = (int)S.tiles.size();
+  P.ndraws = E.ndraws;
+  P.ntiles = E.ntiles;
   P.M = ndens;
   P.L = L;
   P.T = Niter;
@@ -217,9 +319,6 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
   }
   if (e != cudaSuccess) KDE_FAIL(100 + (int)e, "gibbs kernel launch: %s", cudaGetErrorString(e));
   if (launches) *launches += 1;
-  KDE_CUDA(cudaFreeAsync(d_draws, st));
-  KDE_CUDA(cudaFreeAsync(d_tiles, st));
-  KDE_CUDA(cudaFreeAsync(d_counter, st));
   return 0;
 }
 

@@ -40,7 +40,10 @@ namespace kdeb200 {
 constexpr int GB_THREADS = GB_THREADS_N;  // chains per CTA
 constexpr int GB_STAGES = GB_STAGES_N;    // ring depth
 constexpr int GB_TILE_BYTES = GB_TILE_N;  // bytes per ring stage
-constexpr int GB_MAXCK = 64;  // checkpoints per draw
+#ifndef GB_MAXCK_N
+#define GB_MAXCK_N 64
+#endif
+constexpr int GB_MAXCK = GB_MAXCK_N;  // checkpoints per draw (per-thread local memory: 8 bytes each)
 #ifndef GB_UNROLL_A
 #define GB_UNROLL_A 4
 #endif
@@ -372,7 +375,10 @@ __device__ __forceinline__ int pass2(const Draw &dr, const Hoist<D, MASK> &h, co
   return zs;
 }
 
-template <int D, bool MASK>
+// MD = capacity of the per-chain state in densities (4, 8 or 16 >= M): the state lives in per-thread local memory, and
+// sizing it by the call instead of by KDEB200_MAX_DENS keeps the chip-wide local-memory footprint (threads x bytes)
+// inside the L2 next to the trees (ncu: DRAM traffic of the C4 launch, profiles/ncu_issued.json).
+template <int D, bool MASK, int MD>
 __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const __grid_constant__ GibbsParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tiles = reinterpret_cast<double *>(smem_raw);
@@ -392,8 +398,14 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
   // claimed at the start of the LAST draw of the current one (late, so that no CTA hoards work, but early
   // enough for the tile ring to prefetch across the batch boundary).  Chains are addressed by sample index,
   // so the result does not depend on which CTA runs which batch.
+  // Every CTA ends on exactly one failing claim, so a launch performs nbatches + gridDim.x claims in total: the thread
+  // that draws the last ticket puts the counter back to zero for the next launch that is handed this slot (gibbs.cu).
   __shared__ int claim;
-  if (tid == 0) claim = atomicAdd(P.counter, 1);
+  const int last_ticket = P.nbatches + (int)gridDim.x - 1;
+  if (tid == 0) {
+    claim = atomicAdd(P.counter, 1);
+    if (claim == last_ticket) *P.counter = 0;
+  }
   __syncthreads();
   int batch = claim, batch_next = P.nbatches;
   Ring R;
@@ -407,10 +419,10 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
   int64_t q = 0;
 
   // chain state: lambda = 1/variance and lambda*mu of the currently selected node of each density
-  double lam[KDEB200_MAX_DENS * D];
-  double lmu[KDEB200_MAX_DENS * D];
+  double lam[MD * D];
+  double lmu[MD * D];
   double ck[GB_MAXCK];
-  int selpos[KDEB200_MAX_DENS];
+  int selpos[MD];
 
   while (batch < P.nbatches) {
     int64_t s = P.s0 + (int64_t)batch * GB_THREADS + tid;
@@ -440,7 +452,10 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
       const int j = dr.j;
       if (di == P.ndraws - 1) {  // claim the next batch (uniform branch; two barriers around the shared word)
         __syncthreads();
-        if (tid == 0) claim = atomicAdd(P.counter, 1);
+        if (tid == 0) {
+          claim = atomicAdd(P.counter, 1);
+          if (claim == last_ticket) *P.counter = 0;
+        }
         __syncthreads();
         batch_next = claim;
         if (batch_next < P.nbatches) R.known += P.ntiles;
@@ -628,7 +643,10 @@ cudaError_t launch_gibbs_d(const GibbsParams &P, bool masked, int grid_cap, size
     kern<<<grid, GB_THREADS, smem, st>>>(P);
     return cudaGetLastError();
   };
-  return masked ? launch(gibbs_kernel<D, true>) : launch(gibbs_kernel<D, false>);
+  if (masked) return launch(gibbs_kernel<D, true, KDEB200_MAX_DENS>);
+  if (P.M <= 4) return launch(gibbs_kernel<D, false, 4>);
+  if (P.M <= 8) return launch(gibbs_kernel<D, false, 8>);
+  return launch(gibbs_kernel<D, false, KDEB200_MAX_DENS>);
 }
 
 

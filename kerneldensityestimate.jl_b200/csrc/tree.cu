@@ -423,8 +423,11 @@ int tree_on(kdeb200_tree_t t, int slot, kdeb200_tree_t *out) {
   return 0;
 }
 
+void gibbs_invalidate_schedules();  // gibbs.cu: cached schedules hold pointers into tree records
+
 int tree_destroy(kdeb200_tree_t t) {
   if (!t) return 0;
+  if (t->gibbs_ready) gibbs_invalidate_schedules();
   // Kernels of the *_device entry points may still be running on a caller stream: drain the device (microseconds
   // when idle), then release with the stream-ordered allocator (cudaFree cost 33 ms per tree).
   Context &c = ctx();
