@@ -238,12 +238,30 @@ def secondary_single(K, dfma, mufu, args):
                              "unit": "T ex2/s (1 per eval)", "frac": evals / (ms * 1e-3) / mufu, "kernel": "eval_f32_kernel<3,false>"}
             e["max_rel_err_vs_f64"] = float(np.max(np.abs(v - ref) / ref))
         rec[name] = e
+    # the error-bounded tile-pruned route (csrc/eval_pruned.cu; the reference's dual-tree evaluation re-thought for the
+    # GPU): same arithmetic on the pairs it keeps, so the pipe roofline applies to the EVALUATED pairs; the nominal
+    # N x M rate is what a caller sees
+    K.evaluateDualTree(p, pos[:, :8192], precision=K.F64_BOUNDED)
+    t0 = time.perf_counter(); vb = K.evaluateDualTree(p, pos, precision=K.F64_BOUNDED); wall = time.perf_counter() - t0
+    ms, nl = K.last_kernel_ms()
+    kept, redo = K.pruned_stats()
+    rec["f64_bounded"] = {
+        "value": evals / (ms * 1e-3), "unit": "evals/s (nominal N x M)", "kernel_ms": ms, "launches": nl,
+        "kept_pair_fraction": kept, "rows_recomputed_exactly": redo, "evaluated_pairs_per_s": evals * kept / (ms * 1e-3),
+        "max_rel_err_vs_brute_force": float(np.max(np.abs(vb - ref) / ref)), "guaranteed_rel_err": 1e-13,
+        "e2e": {"value": evals / wall, "unit": "evals/s (nominal)", "wall_s": wall, "h2d_bytes": 8 * 3 * M, "d2h_bytes": 8 * M,
+                "api": "kde_b200.evaluateDualTree(precision=F64_BOUNDED) -> kdeb200_eval (host buffers)"},
+        "roofline": {"bound": "fp64_fma_pipe", "note": "on the evaluated pairs (kept fraction of block x tile pairs); includes "
+                     "the Morton sort, box and mask passes in kernel_ms",
+                     "frac": evals * kept * ALG_SLOTS_EVAL[3] / (ms * 1e-3) / dfma},
+        "speedup_vs_brute_force": rec["f64"]["kernel_ms"] / ms}
     o = O.OKDE.kde_bw(pts, bw)
     mq = 128 * cores
     t0 = time.perf_counter(); ov = o.evaluate(pos[:, :mq], nthreads=cores); tn = time.perf_counter() - t0
     rec["cpu_baseline"] = {"value": float(N) * mq / tn, "unit": "evals/s", "cores": cores, "kind": "port",
                            "sample": "%d of %d queries against all %d components in %.1f s (oracle, OpenMP over queries)" % (mq, M, N, tn)}
     rec["parity_max_rel_err_vs_oracle"] = float(np.max(np.abs(ref[:mq] - ov) / ov))
+    rec["f64_bounded"]["parity_max_rel_err_vs_oracle"] = float(np.max(np.abs(vb[:mq] - ov) / ov))
     out["c5"] = rec
     p._invalidate()
     # ---- C3: kde! LOOCV bandwidth selection on 100k synthetic 4-D mixture points
@@ -256,10 +274,16 @@ def secondary_single(K, dfma, mufu, args):
     evals = float(N) * N
     K.kde(pts[:, :3000])
     t0 = time.perf_counter(); pk = K.kde(pts); total = time.perf_counter() - t0
+    K.set_pruning(0)
+    t0 = time.perf_counter(); pk0 = K.kde(pts); total_brute = time.perf_counter() - t0
+    K.set_pruning(1)
     rec = {"workload": "C3: kde!(points) LOOCV bandwidth selection, %d points, 4-D" % N,
            "one_nLOO_LL": {"value": evals / (ms * 1e-3), "unit": "evals/s", "kernel_ms": ms, "wall_ms": one * 1e3, "launches": nl,
                            "H": H, "roofline": eval_roofline("eval_c3", 1, evals, ms, dfma, "eval_kernel<1,6,true>")},
            "full_kde": {"value": total, "unit": "s", "higher_is_better": False, "bandwidth": K.getBW(pk)[:, 0].tolist(),
+                        "brute_force_only_s": total_brute, "bandwidth_brute_force_only": K.getBW(pk0)[:, 0].tolist(),
+                        "note": "default policy: the LOO likelihood uses the error-bounded pruned kernel (<= 1e-13 relative) "
+                                "wherever the bandwidth is small enough to drop tiles, the brute-force kernel otherwise",
                         "api": "kde_b200.kde(points) -> kdeb200_kde_lcv (host points in, d bandwidths out)",
                         "h2d_bytes": 8 * 2 * N * 4, "d2h_bytes": 8 * 4}}
     o1 = O.OKDE.kde_bw(K.getPoints(p1), K.getBW(p1)[:, 0], K.getWeights(p1))

@@ -35,7 +35,9 @@ extern "C" {
 #define KDEB200_MAX_GPUS 16
 
 #define KDEB200_F64 0 /* FP64 arithmetic (parity mode: 1e-12 eval, exact labels) */
-#define KDEB200_F32 1 /* FP32 arithmetic with MUFU ex2 (evaluation only, 1e-5) */
+#define KDEB200_F32 1 /* FP32 arithmetic with MUFU ex2 (evaluation only, 1e-5; far-tail values flush to 0) */
+#define KDEB200_F64_BOUNDED 2 /* FP64, tile-pruned with a guaranteed bound: every value within 1e-13 relative of the
+                                 brute-force sum (the counterpart of the reference's dual-tree evaluation) */
 
 typedef struct kdeb200_tree_s *kdeb200_tree_t; /* opaque device-resident BallTreeDensity */
 
@@ -126,6 +128,19 @@ int kdeb200_philox_streams(uint64_t seed, int64_t Np, int64_t uniforms_per_sampl
  * evaluates bd at its own points leaving each one out (bd === locations), output in original
  * point order. */
 int kdeb200_eval(kdeb200_tree_t bd, const double *pos, int64_t M, int loo, int precision, double *p_out);
+/* Pruning policy (replaces setForceEvalDirect! / FORCE_EVAL_DIRECT src/DualTree01.jl:3-9, and the dual-tree recursion
+ * evaluate :248-299 + recurseMinMax :164-242 it switches on).  The pruned kernel drops (query block, component tile)
+ * pairs whose bounding boxes are so far apart that each kernel value is below 1e-26, and recomputes over all
+ * components every row whose kept sum is too small for that to mean 1e-13 relative: results are within 1e-13 of the
+ * brute-force sum (the reference's dual tree: errTol = 1e-3).
+ *   0  brute force everywhere
+ *   1  (default) pruned kernel for the leave-one-out likelihood (kdeb200_loo_*, kdeb200_kde_lcv*), brute force for
+ *      kdeb200_eval unless precision == KDEB200_F64_BOUNDED
+ *   2  pruned kernel also for every FP64 kdeb200_eval (= setForceEvalDirect!(false))
+ * kdeb200_pruned_stats: fraction of (block, tile) pairs the last pruned call on this device kept, and how many rows
+ * it recomputed exactly. */
+int kdeb200_set_pruning(int mode);
+int kdeb200_pruned_stats(double *kept_fraction, int64_t *redo_rows);
 int kdeb200_eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int precision, double *d_out,
                         void *stream);
 

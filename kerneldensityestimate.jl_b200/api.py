@@ -29,11 +29,11 @@ __all__ = [
     "KDEError", "BallTree", "BallTreeDensity", "kde", "kde_bang", "getPoints", "getBW", "getWeights", "marginal",
     "sample", "rand", "resample", "evaluateDualTree", "evalAvgLogL", "entropy", "kld", "minkld", "nLOO_LL", "golden",
     "ksize", "neighborMinMax", "lcv_bandwidths", "updateBandwidth", "prodAppxMSGibbsS", "Ndim", "Npts", "init", "init_multi", "multi_count", "gibbs_sizes",
-    "philox_streams", "pipe_peak", "last_kernel_ms", "F64", "F32", "prod", "getKDERange", "getKDERangeLinspace",
+    "philox_streams", "pipe_peak", "last_kernel_ms", "F64", "F32", "F64_BOUNDED", "setForceEvalDirect", "set_pruning", "pruned_stats", "prod", "getKDERange", "getKDERangeLinspace",
     "getKDEMax", "getKDEMean", "getKDEfit", "intersIntgAppxIS", "to_string", "from_string",
 ]
 
-F64, F32 = 0, 1
+F64, F32, F64_BOUNDED = 0, 1, 2
 _EUCLID = ("+", "-")
 
 
@@ -58,6 +58,25 @@ def multi_count():
     n = C.c_int(0)
     check(lib().kdeb200_multi_count(C.byref(n)))
     return n.value
+
+
+def setForceEvalDirect(flag):
+    """setForceEvalDirect!(flag) (src/DualTree01.jl:3-9).  True (the reference's default): evaluateDualTree is the
+    brute-force sum.  False: the reference switches to its dual-tree recursion (errTol = 1e-3); here the
+    error-bounded tile-pruned kernel (kdeb200_set_pruning(2): every value within 1e-13 of brute force)."""
+    check(lib().kdeb200_set_pruning(1 if flag else 2))
+
+
+def set_pruning(mode):
+    """kdeb200_set_pruning: 0 brute force everywhere, 1 (default) pruned LOO likelihood only, 2 pruned evaluations too."""
+    check(lib().kdeb200_set_pruning(int(mode)))
+
+
+def pruned_stats():
+    """(fraction of (query block, component tile) pairs the last pruned call kept, rows it recomputed exactly)"""
+    f, r = C.c_double(0), C.c_int64(0)
+    check(lib().kdeb200_pruned_stats(C.byref(f), C.byref(r)))
+    return f.value, r.value
 
 
 def _require_euclidean(**ops):

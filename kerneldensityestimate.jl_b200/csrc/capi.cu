@@ -21,7 +21,15 @@ int tree_destroy(kdeb200_tree_t t);
 int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb200_allreduce_v_fn allreduce, void *user,
             double *bw_std_out, int *ncalls_out);
 int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int64_t q0, bool scatter,
-                const double *bw_var, double *d_out, cudaStream_t st, int *launches);
+                const double *bw_var, double *d_out, cudaStream_t st, int *launches, int prune);
+void set_prune_mode(int m);
+int get_prune_mode();
+int pruned_last_stats(double *kept_fraction, int64_t *redo_rows);
+// precision argument of the evaluation entry points -> (is FP32, prune argument of eval_device)
+static inline int prune_for(int precision) {
+  if (precision == KDEB200_F64_BOUNDED) return 2;
+  return get_prune_mode() >= 2 ? 1 : 0;
+}
 int eval_device_f32(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, double *d_out, cudaStream_t st,
                     int *launches);
 int loo_partial_device(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int64_t j1, double *d_sum, int *d_flag,
@@ -184,8 +192,9 @@ static int eval_host_block(kdeb200_tree_t bd, const double *pos, int64_t a, int6
   KDE_CUDA(dO.alloc(sizeof(double) * n));
   Timer tm(c);
   int launches = 0;
-  int rc = (precision == KDEB200_F64)
-               ? eval_device(loc, dQ.as<double>(), n, loo, a, scatter, nullptr, dO.as<double>(), c.stream, &launches)
+  int rc = (precision != KDEB200_F32)
+               ? eval_device(loc, dQ.as<double>(), n, loo, a, scatter, nullptr, dO.as<double>(), c.stream, &launches,
+                             prune_for(precision))
                : eval_device_f32(loc, dQ.as<double>(), n, loo, dO.as<double>(), c.stream, &launches);
   if (rc) return rc;
   tm.stop();
@@ -361,8 +370,8 @@ int kdeb200_eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int l
   if (loo) M = bd->N;
   int launches = 0;
   int rc;
-  if (precision == KDEB200_F64)
-    rc = eval_device(bd, d_pos, M, loo, 0, true, nullptr, d_out, (cudaStream_t)stream, &launches);
+  if (precision == KDEB200_F64 || precision == KDEB200_F64_BOUNDED)
+    rc = eval_device(bd, d_pos, M, loo, 0, true, nullptr, d_out, (cudaStream_t)stream, &launches, prune_for(precision));
   else if (precision == KDEB200_F32)
     rc = eval_device_f32(bd, d_pos, M, loo, d_out, (cudaStream_t)stream, &launches);
   else
@@ -376,7 +385,8 @@ int kdeb200_eval(kdeb200_tree_t bd, const double *pos, int64_t M, int loo, int p
   if (int rc = ensure_init()) return rc;
   if (!bd || !p_out) KDE_FAIL(2, "eval: NULL argument");
   if (!loo && !pos && M > 0) KDE_FAIL(2, "eval: pos is NULL");
-  if (precision != KDEB200_F64 && precision != KDEB200_F32) KDE_FAIL(3, "eval: unknown precision %d", precision);
+  if (precision != KDEB200_F64 && precision != KDEB200_F32 && precision != KDEB200_F64_BOUNDED)
+    KDE_FAIL(3, "eval: unknown precision %d", precision);
   if (loo) M = bd->N;
   if (M <= 0) return 0;
   // in-process multi-GPU: query rows block-partitioned.  LOO rows are leaf rows: each device returns its block in leaf
@@ -472,6 +482,19 @@ int kdeb200_kde_lcv_sharded(int d, int64_t N, const double *points, int64_t j0, 
   if (!points || !bw_std_out || !allreduce) KDE_FAIL(2, "kde_lcv_sharded: NULL argument");
   ScalarExchange x{allreduce, user};
   return kde_lcv(d, N, points, j0, j1, scalar_exchange_adapter, &x, bw_std_out, nloo_calls_out);
+}
+
+int kdeb200_set_pruning(int mode) {
+  KDE_SERIALISE();
+  if (mode < 0 || mode > 2) KDE_FAIL(3, "set_pruning: mode must be 0, 1 or 2");
+  set_prune_mode(mode);
+  return 0;
+}
+
+int kdeb200_pruned_stats(double *kept_fraction, int64_t *redo_rows) {
+  KDE_SERIALISE();
+  if (int rc = ensure_init()) return rc;
+  return pruned_last_stats(kept_fraction, redo_rows);
 }
 
 int kdeb200_pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms) {

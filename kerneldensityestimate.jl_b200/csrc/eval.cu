@@ -17,51 +17,6 @@
 
 namespace kdeb200 {
 
-constexpr int EV_THREADS = 128;
-constexpr int EV_STAGES = 3;
-constexpr int EV_TILE_BYTES = 8192;
-
-struct EvalParams {
-  const double *comps;    // N records, stride SE
-  const double *queries;  // query i at queries + i*qstride
-  const int64_t *perm;    // LOO: leaf -> original index (output scatter); may be null (leaf order)
-  double *out;            // M results (S == 1) ...
-  double *partial;        // ... or S x M partial sums
-  const double *exptab;
-  ExpConsts ec;
-  int64_t N, M, q0, chunk;
-  int qstride, S, tile_nodes;
-  double ich[KDEB200_MAX_DIM];  // -0.5 / variance_k
-  double norm;                  // (2 pi)^(d/2) prod sqrt(variance_k)
-};
-
-template <int D>
-struct Rec {
-  static constexpr int SE = (D + 2) & ~1;
-};
-
-template <int S>
-__device__ __forceinline__ void load_rec(const double *__restrict__ r, double (&rr)[S]) {
-#pragma unroll
-  for (int k = 0; k < S; k += 2) {
-    const double2 v = *reinterpret_cast<const double2 *>(r + k);
-    rr[k] = v.x;
-    rr[k + 1] = v.y;
-  }
-}
-
-// -0.5 * sum_k (x_k - mu_k)^2 / var_k   (distGauss! exponent, src/DualTree01.jl:32-44)
-template <int D, int S>
-__device__ __forceinline__ double quad(const double (&x)[D], const double (&r)[S], const double *__restrict__ ich) {
-  double acc = 0.0;
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    const double df = __dadd_rn(x[k], -r[k]);
-    acc = __fma_rn(__dmul_rn(df, df), ich[k], acc);
-  }
-  return acc;
-}
-
 #ifndef EV_R
 #define EV_R 2
 #endif
@@ -262,12 +217,26 @@ static cudaError_t launch_eval(int d, const EvalParams &P, dim3 grid, size_t sme
 
 static int queries_per_cta(int d) { return EV_THREADS * ev_q(d); }
 
+int eval_pruned_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int64_t q0, bool scatter,
+                       const double *bw_var, double *d_out, cudaStream_t st, int *launches);
+bool pruning_can_help(const kdeb200_tree_s *bd, const double *bw_var);
+
+// 0: brute force everywhere; 1 (default): the error-bounded tile-pruned kernel (eval_pruned.cu, <= 1e-13 relative)
+// serves the leave-one-out LIKELIHOOD path (nLOO_LL / entropy / kde!(points)); 2: also plain FP64 evaluations --
+// the counterpart of the reference's setForceEvalDirect!(false) (src/DualTree01.jl:3-9)
+static int g_prune_mode = 1;
+void set_prune_mode(int m) { g_prune_mode = m; }
+int get_prune_mode() { return g_prune_mode; }
+
 // Evaluate rows.  loo: rows are bd's own leaves q0..q0+M-1 (d_pos ignored); d_out is written
 // through perm when `scatter`, else in row order.  bw_var overrides the tree's variances.
+// prune: 0 = brute force, 1 = the pruned kernel where it can drop something, 2 = the pruned kernel always.
 int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int64_t q0, bool scatter,
-                const double *bw_var, double *d_out, cudaStream_t st, int *launches) {
+                const double *bw_var, double *d_out, cudaStream_t st, int *launches, int prune) {
   Context &c = ctx();
   if (M <= 0) return 0;
+  if (prune == 2 || (prune == 1 && bd->N >= 4096 && M >= 1024 && pruning_can_help(bd, bw_var)))
+    return eval_pruned_device(bd, d_pos, M, loo, q0, scatter, bw_var, d_out, st, launches);
   const int d = bd->d;
   EvalParams P;
   P.comps = bd->d_leaf;
@@ -327,7 +296,7 @@ int loo_partial_device(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int6
   const int64_t n = j1 - j0;
   double *d_L = nullptr;
   KDE_CUDA(cudaMallocAsync(&d_L, sizeof(double) * (n > 0 ? n : 1), st));
-  int rc = eval_device(bd, nullptr, n, 1, j0, false, bw_var, d_L, st, launches);
+  int rc = eval_device(bd, nullptr, n, 1, j0, false, bw_var, d_L, st, launches, g_prune_mode >= 1 ? 1 : 0);
   if (rc) return rc;
   loglik_reduce_kernel<<<1, 1024, 0, st>>>(d_L, bd->d_leaf, bd->SE, bd->d, j0, n, d_sum, d_flag);
   KDE_CUDA(cudaGetLastError());

@@ -6,6 +6,51 @@
 
 namespace kdeb200 {
 
+constexpr int EV_THREADS = 128;
+constexpr int EV_STAGES = 3;
+constexpr int EV_TILE_BYTES = 8192;
+
+struct EvalParams {
+  const double *comps;    // N records, stride SE
+  const double *queries;  // query i at queries + i*qstride
+  const int64_t *perm;    // LOO: leaf -> original index (output scatter); may be null (leaf order)
+  double *out;            // M results (S == 1) ...
+  double *partial;        // ... or S x M partial sums
+  const double *exptab;
+  ExpConsts ec;
+  int64_t N, M, q0, chunk;
+  int qstride, S, tile_nodes;
+  double ich[KDEB200_MAX_DIM];  // -0.5 / variance_k
+  double norm;                  // (2 pi)^(d/2) prod sqrt(variance_k)
+};
+
+template <int D>
+struct Rec {
+  static constexpr int SE = (D + 2) & ~1;
+};
+
+template <int S>
+__device__ __forceinline__ void load_rec(const double *__restrict__ r, double (&rr)[S]) {
+#pragma unroll
+  for (int k = 0; k < S; k += 2) {
+    const double2 v = *reinterpret_cast<const double2 *>(r + k);
+    rr[k] = v.x;
+    rr[k + 1] = v.y;
+  }
+}
+
+// -0.5 * sum_k (x_k - mu_k)^2 / var_k   (distGauss! exponent, src/DualTree01.jl:32-44)
+template <int D, int S>
+__device__ __forceinline__ double quad(const double (&x)[D], const double (&r)[S], const double *__restrict__ ich) {
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double df = __dadd_rn(x[k], -r[k]);
+    acc = __fma_rn(__dmul_rn(df, df), ich[k], acc);
+  }
+  return acc;
+}
+
 // Rows whose fast-path total is below EV_TINY (density < 1e-275: the point is > 35 bandwidths away from
 // every component) are recomputed here with libdevice exp, sequentially in leaf order, so that
 // subnormal values and exact zeros (the likelihood's zero rule) match the reference.

@@ -417,6 +417,7 @@ int tree_on(kdeb200_tree_t t, int slot, kdeb200_tree_t *out) {
   rebase(r->d_leaf);
   rebase(r->d_perm);
   r->d_leaf32 = nullptr;
+  r->d_tilebox = nullptr;
   r->slot = slot;
   t->replica[slot] = r;
   *out = r;
@@ -438,6 +439,7 @@ int tree_destroy(kdeb200_tree_t t) {
   const double t1 = now();
   if (t->d_base) cudaFreeAsync(t->d_base, c.stream);
   if (t->d_leaf32) cudaFreeAsync(t->d_leaf32, c.stream);
+  if (t->d_tilebox) cudaFreeAsync(t->d_tilebox, c.stream);
   for (int s = 1; s < KDEB200_MAX_GPUS; ++s)
     if (kdeb200_tree_s *r = t->replica[s]) {
       if (s < multi_count() && ctx_at(s).ready) {  // the context may be gone after a re-init: its memory went with it
@@ -445,6 +447,7 @@ int tree_destroy(kdeb200_tree_t t) {
         cudaDeviceSynchronize();
         if (r->d_base) cudaFreeAsync(r->d_base, ctx_at(s).stream);
         if (r->d_leaf32) cudaFreeAsync(r->d_leaf32, ctx_at(s).stream);
+        if (r->d_tilebox) cudaFreeAsync(r->d_tilebox, ctx_at(s).stream);
       }
       delete r;
     }

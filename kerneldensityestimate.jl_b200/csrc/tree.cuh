@@ -40,6 +40,8 @@ struct kdeb200_tree_s {
   double *d_leaf = nullptr;     // leaf order (N+1..2N): [x_0..x_{d-1}, w], stride SE -- evalDirect's order
   int64_t *d_perm = nullptr;    // leaf order: original 0-based index
   float *d_leaf32 = nullptr;    // lazily built FP32 shadow of d_leaf (centred, pre-scaled), eval_f32.cu
+  double *d_tilebox = nullptr;  // lazily built bounding boxes + weight sums of the component tiles (eval_pruned.cu)
+  double wtotal = 0.0;          // sum_i |w_i| (error bound of the pruned evaluation)
   size_t device_bytes = 0;
   int slot = 0;                 // context slot that owns the device memory (0 = primary)
   std::vector<int64_t> h_perm;  // host copy of d_perm (scatter of sharded LOO rows)
