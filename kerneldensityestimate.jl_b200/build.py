@@ -43,9 +43,20 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_variant(tag, defines):
-    """Experimental builds (tuning sweeps): libkdeb200_<tag>.so with extra -D flags; selected at run
-    time with KDEB200_SO=<path>."""
+def build_variant(tag, defines, tuned=None):
+    """Experimental builds (tuning sweeps): libkdeb200_<tag>.so with extra -D flags on the sources in `tuned`
+    (default: the Gibbs kernel); selected at run time with KDEB200_SO=<path>."""
+    global GIBBS_TUNED
+    saved = GIBBS_TUNED
+    if tuned is not None:
+        GIBBS_TUNED = list(tuned)
+    try:
+        return _build_variant(tag, defines)
+    finally:
+        GIBBS_TUNED = saved
+
+
+def _build_variant(tag, defines):
     out = os.path.join(HERE, "libkdeb200_%s.so" % tag)
     bdir = os.path.join(HERE, "build", tag)
     os.makedirs(bdir, exist_ok=True)

@@ -220,6 +220,8 @@ static int queries_per_cta(int d) { return EV_THREADS * ev_q(d); }
 int eval_pruned_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int64_t q0, bool scatter,
                        const double *bw_var, double *d_out, cudaStream_t st, int *launches);
 bool pruning_can_help(const kdeb200_tree_s *bd, const double *bw_var);
+bool loo_sym_applicable(const kdeb200_tree_s *bd);
+int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStream_t st, int *launches);
 
 // 0: brute force everywhere; 1 (default): the error-bounded tile-pruned kernel (eval_pruned.cu, <= 1e-13 relative)
 // serves the leave-one-out LIKELIHOOD path (nLOO_LL / entropy / kde!(points)); 2: also plain FP64 evaluations --
@@ -235,7 +237,8 @@ int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int6
                 const double *bw_var, double *d_out, cudaStream_t st, int *launches, int prune) {
   Context &c = ctx();
   if (M <= 0) return 0;
-  if (prune == 2 || (prune == 1 && bd->N >= 4096 && M >= 1024 && pruning_can_help(bd, bw_var)))
+  // the pruned kernel has one CTA per block of 256 queries (no component splits): it needs enough blocks to fill the chip
+  if (prune == 2 || (prune == 1 && bd->N >= 4096 && M >= (int64_t)512 * c.sm_count && pruning_can_help(bd, bw_var)))
     return eval_pruned_device(bd, d_pos, M, loo, q0, scatter, bw_var, d_out, st, launches);
   const int d = bd->d;
   EvalParams P;
@@ -296,7 +299,13 @@ int loo_partial_device(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int6
   const int64_t n = j1 - j0;
   double *d_L = nullptr;
   KDE_CUDA(cudaMallocAsync(&d_L, sizeof(double) * (n > 0 ? n : 1), st));
-  int rc = eval_device(bd, nullptr, n, 1, j0, false, bw_var, d_L, st, launches, g_prune_mode >= 1 ? 1 : 0);
+  // all rows of one density on one device: each unordered pair once (symmetric kernel); row ranges (multi-GPU shards)
+  // and small / very large densities: the row-by-row kernels
+  int rc;
+  if (g_prune_mode >= 1 && j0 == 0 && j1 == bd->N && loo_sym_applicable(bd))
+    rc = loo_sym_device(bd, bw_var, d_L, st, launches);
+  else
+    rc = eval_device(bd, nullptr, n, 1, j0, false, bw_var, d_L, st, launches, g_prune_mode >= 1 ? 1 : 0);
   if (rc) return rc;
   loglik_reduce_kernel<<<1, 1024, 0, st>>>(d_L, bd->d_leaf, bd->SE, bd->d, j0, n, d_sum, d_flag);
   KDE_CUDA(cudaGetLastError());

@@ -126,3 +126,29 @@ def test_bounded_eval_sharded_in_process():
         assert relerr(got, K.evaluateDualTree(p, pos)) < 1e-13 and relerr(loo, K.evaluateDualTree(p, p)) < 1e-13
     finally:
         K.init_multi(1)
+
+
+@pytest.mark.parametrize("d,N,scale", [(1, 5000, 0.3), (1, 100_000, 1.0), (2, 12_345, 0.5), (3, 9_000, 1.0), (4, 7_001, 1.0), (7, 4_500, 1.0)])
+def test_symmetric_loo_likelihood_matches_reference_order_kernel_and_oracle(d, N, scale):
+    """The each-pair-once LOO kernel (loo_sym_kernel) that serves entropy / nLOO_LL for 4096 <= N <= 262144 against
+    the reference-order brute-force kernel (kdeb200_set_pruning(0)) and the oracle's literal rows: non-uniform
+    weights, ragged sizes (row blocks, tiles and N all out of step), bandwidths with and without anything to prune."""
+    rng = np.random.default_rng(100 * d + N)
+    pts = mixture(rng, d, N)
+    w = rng.random(N) + 0.05
+    bw = silverman(pts) * scale
+    p = K.kde(pts, bw, w)
+    K.set_pruning(0)
+    H0 = K.entropy(p)
+    K.set_pruning(1)
+    H1 = K.entropy(p)
+    assert abs(H1 - H0) <= 2e-13 * abs(H0), (H0, H1)
+    for a in (0.3, 2.5):                                   # nLOO_LL multiplies the bandwidth: narrow and wide kernels
+        K.set_pruning(0)
+        r0 = K.nLOO_LL(a, p)
+        K.set_pruning(1)
+        r1 = K.nLOO_LL(a, p)
+        assert abs(r1 - r0) <= 2e-13 * abs(r0)
+    if N <= 20_000:
+        o = OKDE.kde_bw(pts, bw, w)
+        assert abs(H1 - o.entropy()) <= 1e-12 * abs(H1)
