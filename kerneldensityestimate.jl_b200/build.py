@@ -63,8 +63,8 @@ def _build_variant(tag, defines):
     procs, objs = [], []
     build()
     for s in SOURCES:
-        if s not in GIBBS_TUNED:  # the tuning knobs only touch the Gibbs kernel
-            if not s.startswith("gibbs_d"):
+        if s not in GIBBS_TUNED:  # everything else comes from the main build
+            if not (s.startswith("gibbs_d") and any("GB_ONLY_D3" in d for d in defines)):
                 objs.append(os.path.join(HERE, "build", s.replace(".cu", ".o")))
             continue
         o = os.path.join(bdir, s.replace(".cu", ".o"))

@@ -2,6 +2,7 @@
 // The kernel lives in gibbs_kernel.cuh and is instantiated once per dimension in gibbs_d<N>.cu.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <mutex>
@@ -19,6 +20,15 @@ extern template cudaError_t launch_gibbs_d<5>(const GibbsParams &, bool, int, si
 extern template cudaError_t launch_gibbs_d<6>(const GibbsParams &, bool, int, size_t, cudaStream_t, int);
 extern template cudaError_t launch_gibbs_d<7>(const GibbsParams &, bool, int, size_t, cudaStream_t, int);
 extern template cudaError_t launch_gibbs_d<8>(const GibbsParams &, bool, int, size_t, cudaStream_t, int);
+
+extern template cudaError_t launch_gibbs_warp_d<1>(const GibbsParams &, bool, int, cudaStream_t);
+extern template cudaError_t launch_gibbs_warp_d<2>(const GibbsParams &, bool, int, cudaStream_t);
+extern template cudaError_t launch_gibbs_warp_d<3>(const GibbsParams &, bool, int, cudaStream_t);
+extern template cudaError_t launch_gibbs_warp_d<4>(const GibbsParams &, bool, int, cudaStream_t);
+extern template cudaError_t launch_gibbs_warp_d<5>(const GibbsParams &, bool, int, cudaStream_t);
+extern template cudaError_t launch_gibbs_warp_d<6>(const GibbsParams &, bool, int, cudaStream_t);
+extern template cudaError_t launch_gibbs_warp_d<7>(const GibbsParams &, bool, int, cudaStream_t);
+extern template cudaError_t launch_gibbs_warp_d<8>(const GibbsParams &, bool, int, cudaStream_t);
 
 __global__ void philox_streams_kernel(uint64_t seed, int64_t Np, int64_t perU, int64_t perN, double *U, double *G) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,6 +310,36 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
     P.root_rec[j] = t->d_buf + t->levels[0].offC;
     P.labels[j] = t->d_labels;
     for (int k = 0; k < d; ++k) P.hvar[j][k] = t->hvar[k];
+  }
+  // Few chains: one warp per chain (K1w).  The thread-per-chain kernel needs ~128 x 4 x SMs chains to fill the chip;
+  // below ~96 chains per SM the warp kernel finishes sooner (KDEB200_GIBBS_WARP_MAX overrides; 0 disables it).  Its
+  // prefix sums live in shared memory, which bounds the level size.
+  {
+    int nmax = 1;
+    for (int j = 0; j < ndens; ++j)
+      if (trees[j]->levels[trees[j]->depth].n > nmax) nmax = (int)trees[j]->levels[trees[j]->depth].n;
+    int64_t warp_max = (int64_t)96 * c.sm_count;
+    if (const char *ev = getenv("KDEB200_GIBBS_WARP_MAX")) warp_max = atoll(ev);
+    if (s1 - s0 <= warp_max && gibbs_warp_smem(d, nmax) <= 96 * 1024) {
+      cudaError_t we = cudaErrorInvalidValue;
+      switch (d) {
+#ifdef GB_ONLY_D3
+        case 3: we = launch_gibbs_warp_d<3>(P, masked, nmax, st); break;
+#else
+        case 1: we = launch_gibbs_warp_d<1>(P, masked, nmax, st); break;
+        case 2: we = launch_gibbs_warp_d<2>(P, masked, nmax, st); break;
+        case 3: we = launch_gibbs_warp_d<3>(P, masked, nmax, st); break;
+        case 4: we = launch_gibbs_warp_d<4>(P, masked, nmax, st); break;
+        case 5: we = launch_gibbs_warp_d<5>(P, masked, nmax, st); break;
+        case 6: we = launch_gibbs_warp_d<6>(P, masked, nmax, st); break;
+        case 7: we = launch_gibbs_warp_d<7>(P, masked, nmax, st); break;
+        case 8: we = launch_gibbs_warp_d<8>(P, masked, nmax, st); break;
+#endif
+      }
+      if (we != cudaSuccess) KDE_FAIL(100 + (int)we, "gibbs (warp per chain) kernel launch: %s", cudaGetErrorString(we));
+      if (launches) *launches += 1;
+      return 0;
+    }
   }
   const size_t smem = GB_STAGES * GB_TILE_BYTES;
   cudaError_t e = cudaErrorInvalidValue;

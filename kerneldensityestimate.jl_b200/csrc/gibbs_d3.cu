@@ -2,4 +2,5 @@
 #include "gibbs_kernel.cuh"
 namespace kdeb200 {
 template cudaError_t launch_gibbs_d<3>(const GibbsParams &, bool, int, size_t, cudaStream_t, int);
+template cudaError_t launch_gibbs_warp_d<3>(const GibbsParams &, bool, int, cudaStream_t);
 }

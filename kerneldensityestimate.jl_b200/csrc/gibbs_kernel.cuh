@@ -650,4 +650,250 @@ cudaError_t launch_gibbs_d(const GibbsParams &P, bool masked, int grid_cap, size
 }
 
 
+
+// ================================================================ K1w: one WARP per chain ======================
+// The small configurations the reference is actually used for (products of a few densities of ~100 components, 100 to
+// a few thousand samples: SURVEY.md C1 / C2) cannot fill the chip with one thread per chain -- 100 samples are one CTA
+// on one SM, and the call is the latency of one thread walking 2 712 dependent kernel evaluations.  Here a warp owns a
+// chain: the lanes evaluate the nodes of a level in parallel (coalesced record reads, p[z] to shared memory), ONE lane
+// then adds them up sequentially in node order -- the same additions in the same order as the one-thread kernel and
+// the reference, so pT, the CDF and hence the labels are bit-identical -- and the lanes search the prefix sums for
+// u * pT in parallel.  Same schedule, same records, same eval_node arithmetic, same RNG addressing as gibbs_kernel;
+// used when the call has too few chains for the thread-per-chain kernel (gibbs.cu picks).
+constexpr int GW_WARPS = 4;  // chains per CTA
+
+template <int D, bool MASK>
+__global__ void __launch_bounds__(GW_WARPS * 32) gibbs_warp_kernel(const __grid_constant__ GibbsParams P, int nmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(16) double tab[KDE_EXP_TAB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = P.M;
+  for (int i = tid; i < KDE_EXP_TAB; i += GW_WARPS * 32) tab[i] = P.exptab[i];
+  __syncthreads();
+  // per-warp shared memory: prefix sums | lam | lmu | X | selpos
+  const size_t per_warp = (size_t)nmax + 2 * KDEB200_MAX_DENS * D + D + KDEB200_MAX_DENS / 2 + 2;
+  double *pbuf = reinterpret_cast<double *>(smem_raw) + (size_t)warp * per_warp;
+  double *lam = pbuf + nmax, *lmu = lam + KDEB200_MAX_DENS * D, *X = lmu + KDEB200_MAX_DENS * D;
+  int *selpos = reinterpret_cast<int *>(X + D + 1);
+  const unsigned FULL = 0xffffffffu;
+
+  const int64_t s = P.s0 + (int64_t)blockIdx.x * GW_WARPS + warp;
+  if (s >= P.s1) return;  // whole warp; no block-level barrier below
+
+  for (int i = lane; i < M * D; i += 32) {  // levelInit!/initIndices!/calcIndices!: every density starts at the root
+    const int j = i / D, k = i % D;
+    const double *rr = P.root_rec[j];
+    if (MASK && !P.mask[j][k]) {
+      lam[i] = 0.0;
+      lmu[i] = 0.0;
+    } else {
+      const double l = 1.0 / rr[D + k];
+      lam[i] = l;
+      lmu[i] = rr[k] * l;
+    }
+  }
+  if (lane < M) selpos[lane] = 0;
+  __syncwarp();
+
+  for (int di = 0; di < P.ndraws; ++di) {
+    const Draw dr = P.draws[di];
+    const int j = dr.j;
+    if (dr.new_level) {  // samplePoint!(addEntropy = true): lane k owns dimension k
+      if (lane < D) {
+        const int k = lane;
+        double Lm = 0.0, Hm = 0.0;
+        bool any = !MASK;
+        for (int i = 0; i < M; ++i) {
+          if (MASK && P.mask[i][k]) any = true;
+          Lm += lam[i * D + k];
+          Hm += lmu[i * D + k];
+        }
+        const uint32_t slot = (uint32_t)((dr.level - 1) * D + k);
+        const double g = P.randN ? P.randN[s * P.perN + slot] : philox_normal(P.seed, (uint64_t)s, slot);
+        double v = 0.0;
+        if (any) {
+          const double cov = 1.0 / Lm;
+          v = cov * Hm + sqrt(cov) * g;
+        }
+        X[k] = v;
+      }
+      __syncwarp();
+    }
+
+    // the per-draw constants: lane k computes dimension k, then everybody gets a copy
+    double mu_k = 0.0, cadd_k = 0.0, ich_k = 0.0, c_k = 1.0;
+    bool act_k = true;
+    if (lane < D) {
+      const int k = lane;
+      if (dr.kind == 0) {
+        mu_k = X[k];
+        cadd_k = 0.0;
+        act_k = MASK ? (P.mask[j][k] && P.other[j][k]) : true;
+      } else {
+        double Lm = 0.0, Hm = 0.0;
+        for (int i = 0; i < M; ++i) {
+          if (i == j) continue;
+          Lm += lam[i * D + k];
+          Hm += lmu[i * D + k];
+        }
+        const bool oth = MASK ? (P.other[j][k] != 0) : (M > 1);
+        if (oth) {
+          const double cov = 1.0 / Lm;
+          cadd_k = cov;
+          mu_k = cov * Hm;
+        }
+        act_k = (MASK ? (P.mask[j][k] != 0) : true) && oth;
+      }
+      if (dr.variant == VAR_A) {
+        c_k = P.hvar[j][k] + cadd_k;
+        ich_k = sqrt(0.5 / c_k);
+      }
+    }
+    Hoist<D, MASK> h;
+    double scale = 1.0;
+    {
+      double prod = 1.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        h.mu[k] = __shfl_sync(FULL, mu_k, k);
+        h.cadd[k] = __shfl_sync(FULL, cadd_k, k);
+        h.ich[k] = __shfl_sync(FULL, ich_k, k);
+        h.act[k] = __shfl_sync(FULL, (int)act_k, k) != 0;
+        const double c = __shfl_sync(FULL, c_k, k);
+        if (!MASK || h.act[k]) prod *= c;  // same order of multiplications as gibbs_kernel
+      }
+      if (dr.variant == VAR_A) scale = kde_rsqrt(prod);
+    }
+
+    // pass 1, parallel part: p[z]
+    const int n = dr.n;
+    for (int z = lane; z < n; z += 32) {
+      const double *r = dr.rec + (size_t)z * dr.stride;
+      double p;
+      if (dr.variant == VAR_A) p = eval_node<D, MASK, VAR_A>(r, h, tab, P.ec);
+      else if (dr.variant == VAR_B) p = eval_node<D, MASK, VAR_B>(r, h, tab, P.ec);
+      else p = eval_node<D, MASK, VAR_C>(r, h, tab, P.ec);
+      pbuf[z] = p;
+    }
+    __syncwarp();
+    // pass 1, sequential part: running sums in node order (one lane; 4 loads in flight ahead of the adds)
+    double pT = 0.0;
+    if (lane == 0) {
+      double S = 0.0;
+      int z = 0;
+      for (; z + 4 <= n; z += 4) {
+        const double a0 = pbuf[z], a1 = pbuf[z + 1], a2 = pbuf[z + 2], a3 = pbuf[z + 3];
+        S = __dadd_rn(S, a0); pbuf[z] = S;
+        S = __dadd_rn(S, a1); pbuf[z + 1] = S;
+        S = __dadd_rn(S, a2); pbuf[z + 2] = S;
+        S = __dadd_rn(S, a3); pbuf[z + 3] = S;
+      }
+      for (; z < n; ++z) {
+        S = __dadd_rn(S, pbuf[z]);
+        pbuf[z] = S;
+      }
+      pT = S;
+    }
+    pT = __shfl_sync(FULL, pT, 0);
+    __syncwarp();
+
+    // selectLabelOnLevel
+    int zs = 0;
+    if (n > 1) {
+      const uint32_t c = (uint32_t)(M + di);
+      const double u = P.randU ? P.randU[s * P.perU + c - 1] : philox_uniform(P.seed, (uint64_t)s, c);
+      if (pT * scale < 1e-99) {  // :311-315: all p[z] = weight(last node); rare, one lane
+        if (lane == 0) {
+          const double w = dr.wts[n - 1];
+          double tot = 0.0;
+          for (int z = 0; z < n; ++z) tot += w;
+          const double qv = w / tot;
+          double cdf = 0.0;
+          zs = n - 1;
+          bool found = false;
+          for (int z = 0; z < n - 1; ++z) {
+            cdf += qv;
+            if (!found && u <= cdf) {
+              zs = z;
+              found = true;
+            }
+          }
+        }
+        zs = __shfl_sync(FULL, zs, 0);
+      } else {
+        const double target = u * pT;
+        unsigned best = (unsigned)(n - 1);
+        for (int z = lane; z < n; z += 32)
+          if (target <= pbuf[z]) {
+            best = (unsigned)z;
+            break;
+          }
+        zs = (int)__reduce_min_sync(FULL, best);
+      }
+    }
+    __syncwarp();  // pbuf is rewritten by the next draw
+    if (lane == 0) {
+      selpos[j] = zs;
+      if (P.level_labels && dr.kind == 1) P.level_labels[((s - P.s0) * M + j) * P.L + (dr.level - 1)] = dr.levperm[zs];
+    }
+    if (lane < D) {  // updateGlbParticlesVariance!(j)
+      const int k = lane;
+      const double *rs = dr.rec_state + (size_t)zs * dr.state_stride;
+      if (MASK && !P.mask[j][k]) {
+        lam[j * D + k] = 0.0;
+        lmu[j * D + k] = 0.0;
+      } else {
+        const double var = dr.state_has_bw ? rs[D + k] : P.hvar[j][k];
+        const double l = 1.0 / var;
+        lam[j * D + k] = l;
+        lmu[j * D + k] = rs[k] * l;
+      }
+    }
+    __syncwarp();
+  }
+
+  // labels (:612-616) and the final samplePoint! (:625)
+  const int64_t o = s - P.s0;
+  if (lane < M) P.indices[o * M + lane] = P.labels[lane][selpos[lane]];
+  if (lane < D) {
+    const int k = lane;
+    double Lm = 0.0, Hm = 0.0;
+    bool any = !MASK;
+    for (int i = 0; i < M; ++i) {
+      if (MASK && P.mask[i][k]) any = true;
+      Lm += lam[i * D + k];
+      Hm += lmu[i * D + k];
+    }
+    double v = 0.0;
+    if (any) {
+      const double cov = 1.0 / Lm;
+      v = cov * Hm;
+      if (P.add_entropy) {
+        const uint32_t slot = (uint32_t)(P.L * D + k);
+        const double g = P.randN ? P.randN[s * P.perN + slot] : philox_normal(P.seed, (uint64_t)s, slot);
+        v = v + sqrt(cov) * g;
+      }
+    }
+    P.points[o * D + k] = v;
+  }
+}
+
+inline size_t gibbs_warp_smem(int d, int nmax) {
+  return sizeof(double) * GW_WARPS * ((size_t)nmax + 2 * KDEB200_MAX_DENS * d + d + KDEB200_MAX_DENS / 2 + 2);
+}
+
+template <int D>
+cudaError_t launch_gibbs_warp_d(const GibbsParams &P, bool masked, int nmax, cudaStream_t st) {
+  const size_t smem = gibbs_warp_smem(D, nmax);
+  const int64_t n = P.s1 - P.s0;
+  const unsigned grid = (unsigned)((n + GW_WARPS - 1) / GW_WARPS);
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, GW_WARPS * 32, smem, st>>>(P, nmax);
+    return cudaGetLastError();
+  };
+  return masked ? launch(gibbs_warp_kernel<D, true>) : launch(gibbs_warp_kernel<D, false>);
+}
+
 }  // namespace kdeb200
