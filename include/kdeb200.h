@@ -144,6 +144,18 @@ int kdeb200_pruned_stats(double *kept_fraction, int64_t *redo_rows);
 int kdeb200_eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int precision, double *d_out,
                         void *stream);
 
+/* Every 1-D marginal of bd evaluated on its own grid in ONE launch, straight from the d-dimensional records: replaces
+ * the per-dimension `mm = marginal(p,[i]); mm(X)` of getKDEMax (src/DualTree01.jl:558-569, marginal src/KDE01.jl:143-153),
+ * which builds a 1-D tree per dimension to evaluate 200 points.  grids and out are d x G, row k = dimension k. */
+int kdeb200_eval_marginals(kdeb200_tree_t bd, const double *grids, int64_t G, double *out);
+
+/* sample(npd, Npts) (src/KDE01.jl:164-183; rand :196-198, resample src/BallTreeDensity01.jl:312-334): component indices
+ * by inverse CDF from SORTED uniforms over the cumulative weights in original point order, plus the Gaussian kernel
+ * perturbation bw .* randn.  randU (Np uniforms, any order -- they are sorted like the reference's sort(rand(Npts))) and
+ * randN (d x Np, column-major) inject the variates; NULL draws them from Philox4x32-10(seed).  ind_out is 1-based. */
+int kdeb200_sample(kdeb200_tree_t bd, int64_t Np, uint64_t seed, const double *randU, const double *randN,
+                   double *points_out, int64_t *ind_out);
+
 /* ---- S3: leave-one-out likelihood (fused) --------------------------------------------------
  * Replaces entropy(bd) src/DualTree01.jl:505-508 / evalAvgLogL :450-470 as called from
  * nLOO_LL src/CrossValidation.jl:15-24.  bw_var (d variances) overrides the tree's leaf

@@ -49,6 +49,8 @@ SIGNATURES = {
                                           C.POINTER(C.c_int)]),
     "kdeb200_kde_lcv_sharded_v": (C.c_int, [C.c_int, C.c_int64, f64p, C.c_int64, C.c_int64, allreduce_v_fn, C.c_void_p, f64p,
                                             C.POINTER(C.c_int)]),
+    "kdeb200_eval_marginals": (C.c_int, [tree_t, f64p, C.c_int64, f64p]),
+    "kdeb200_sample": (C.c_int, [tree_t, C.c_int64, C.c_uint64, f64p, f64p, f64p, i64p]),
     "kdeb200_set_pruning": (C.c_int, [C.c_int]),
     "kdeb200_pruned_stats": (C.c_int, [f64p, i64p]),
     "kdeb200_pipe_peak": (C.c_int, [C.c_int, C.c_int, f64p, f64p]),

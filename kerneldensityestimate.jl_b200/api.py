@@ -30,7 +30,7 @@ __all__ = [
     "sample", "rand", "resample", "evaluateDualTree", "evalAvgLogL", "entropy", "kld", "minkld", "nLOO_LL", "golden",
     "ksize", "neighborMinMax", "lcv_bandwidths", "updateBandwidth", "prodAppxMSGibbsS", "Ndim", "Npts", "init", "init_multi", "multi_count", "gibbs_sizes",
     "philox_streams", "pipe_peak", "last_kernel_ms", "F64", "F32", "F64_BOUNDED", "setForceEvalDirect", "set_pruning", "pruned_stats", "prod", "getKDERange", "getKDERangeLinspace",
-    "getKDEMax", "getKDEMean", "getKDEfit", "intersIntgAppxIS", "to_string", "from_string",
+    "getKDEMax", "getKDEMean", "getKDEfit", "intersIntgAppxIS", "eval_marginals", "to_string", "from_string",
 ]
 
 F64, F32, F64_BOUNDED = 0, 1, 2
@@ -297,44 +297,42 @@ def marginal(bd, ind):
     return kde(pts[ind - 1, :], sig[ind - 1, 0], wts)
 
 
-def sample(npd, Npts_, ind=None, rng=None):
-    """src/KDE01.jl:164-189.  Julia's global RNG is not reproducible outside Julia; pass a
-    numpy Generator for repeatability."""
-    rng = np.random.default_rng() if rng is None else rng
-    pts = getPoints(npd)
+def sample(npd, Npts_, ind=None, rng=None, seed=None):
+    """sample(npd, Npts[, ind]) (src/KDE01.jl:164-189) on the device (kdeb200_sample): inverse-CDF component draw from
+    sorted uniforms over the cumulative weights in original point order + the kernel perturbation.  Julia's global RNG
+    is not reproducible outside Julia: pass a numpy Generator `rng` (its uniforms / normals are injected) or a `seed`
+    for the library's Philox streams.  Returns (points d x Npts, ind 1-based)."""
     d = npd.bt.dims
-    bw = getBW(npd)
-    if ind is not None:
+    if ind is not None:  # explicit components: no search, just the perturbation (src/KDE01.jl:185-189)
+        rng = np.random.default_rng(seed) if rng is None else rng
         ind = np.asarray(ind, dtype=np.int64)
-        return pts[:, ind - 1] + bw[:, ind - 1] * rng.standard_normal((d, len(ind))), ind
-    w = np.cumsum(getWeights(npd))
-    w = w / w[-1]
-    randnums = rng.standard_normal((d, Npts_))
-    t = np.concatenate([np.sort(rng.random(Npts_)), [10.0]])
-    points = np.zeros((d, Npts_))
+        return getPoints(npd)[:, ind - 1] + getBW(npd)[:, ind - 1] * rng.standard_normal((d, len(ind))), ind
+    Npts_ = int(Npts_)
+    pts = np.zeros((Npts_, d))
     idx = np.zeros(Npts_, dtype=np.int64)
-    ii = 0
-    for i in range(pts.shape[1]):
-        while w[i] > t[ii]:
-            points[:, ii] = pts[:, i] + bw[:, i] * randnums[:, ii]
-            idx[ii] = i + 1
-            ii += 1
-    return points, idx
+    U = G = None
+    if rng is not None:
+        G = np.ascontiguousarray(rng.standard_normal((d, Npts_)).T).ravel()   # randn(d, Npts), column-major
+        U = np.ascontiguousarray(rng.random(Npts_))
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    check(lib().kdeb200_sample(npd._dev(), Npts_, int(seed) & 0xFFFFFFFFFFFFFFFF, fptr(U), fptr(G), fptr(pts), iptr(idx)))
+    return pts.T, idx
 
 
-def rand(p, N=1, rng=None):
+def rand(p, N=1, rng=None, seed=None):
     """src/KDE01.jl:196-198"""
-    return sample(p, N, rng=rng)[0]
+    return sample(p, N, rng=rng, seed=seed)[0]
 
 
-def resample(p, Np=-1, ksType="lcv", rng=None):
+def resample(p, Np=-1, ksType="lcv", rng=None, seed=None):
     """src/BallTreeDensity01.jl:312-334.  The reference's default Np=-1 and :discrete branches call
     undefined getNpts/getDim and throw; here Np=-1 means Npts(p) and :discrete is rejected."""
     if Np == -1:
         Np = Npts(p)
     if ksType in ("discrete", ":discrete"):
         raise KDEError("resample: ksType=:discrete is broken in the reference (undefined getDim) and not provided")
-    samplePts, _ = sample(p, Np, rng=rng)
+    samplePts, _ = sample(p, Np, rng=rng, seed=seed)
     return kde(samplePts)
 
 
@@ -443,15 +441,26 @@ def getKDERangeLinspace(bd, extend=0.1, N=200):
 
 
 def getKDEMax(p, N=200):
-    """src/DualTree01.jl:558-569: per-dimension argmax of the marginal on an N-point grid."""
-    m = np.zeros(Ndim(p))
-    for i in range(Ndim(p)):
-        mm = marginal(p, [i + 1])
-        r = getKDERange(mm).ravel(order="F")
-        X = np.linspace(r[0], r[1], N)
-        yV = mm(X.reshape(1, N))
-        m[i] = X[int(np.argmax(yV))]
-    return m
+    """src/DualTree01.jl:558-569: per-dimension argmax of the marginal on an N-point grid.  The reference builds one
+    marginal tree per dimension and evaluates it; here all d marginals are evaluated on their grids in one launch
+    (kdeb200_eval_marginals), straight from the d-dimensional density."""
+    d = Ndim(p)
+    pts = getPoints(p)
+    lo, hi = pts.min(axis=1), pts.max(axis=1)          # getKDERange(marginal(p,[i])) with extend = 0.1
+    dr = 0.1 * (hi - lo)
+    X = np.stack([np.linspace(lo[i] - dr[i], hi[i] + dr[i], N) for i in range(d)])
+    Y = eval_marginals(p, X)
+    return np.array([X[i, int(np.argmax(Y[i]))] for i in range(d)])
+
+
+def eval_marginals(p, grids):
+    """Densities of every 1-D marginal of p on its own grid: grids is d x G (row k = abscissae of dimension k)."""
+    g = np.ascontiguousarray(grids, dtype=np.float64)
+    if g.ndim != 2 or g.shape[0] != Ndim(p):
+        raise KDEError("eval_marginals: grids must be a %d x G matrix" % Ndim(p))
+    out = np.zeros_like(g)
+    check(lib().kdeb200_eval_marginals(p._dev(), fptr(g), g.shape[1], fptr(out)))
+    return out
 
 
 def getKDEMean(p):
@@ -479,11 +488,15 @@ def intersIntgAppxIS(p, q, N=201):
     if nd == 1:
         yy = evaluateDualTree(p, xx) * evaluateDualTree(q, xx)
         return float(np.sum(yy) * dx[0])
+    # the reference evaluates row by row (2 N calls of N points, src/DualTree01.jl:605-613); one call per density over
+    # the whole N x N grid gives the same values, then the same row-wise accumulation
+    grid = np.empty((2, N * N))
+    grid[0] = np.tile(LD[0], N)
+    grid[1] = np.repeat(LD[1], N)
+    yy = (evaluateDualTree(p, grid) * evaluateDualTree(q, grid)).reshape(N, N)
     acc = 0.0
     for i in range(N):
-        xx[1, :] = LD[1][i]
-        yy = evaluateDualTree(p, xx) * evaluateDualTree(q, xx)
-        acc += (dx[0] * float(np.sum(yy))) * dx[1]
+        acc += (dx[0] * float(np.sum(yy[i]))) * dx[1]
     return acc
 
 

@@ -22,6 +22,9 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
             double *bw_std_out, int *ncalls_out);
 int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int64_t q0, bool scatter,
                 const double *bw_var, double *d_out, cudaStream_t st, int *launches, int prune);
+int eval_marginals_device(kdeb200_tree_t bd, const double *d_grid, int64_t G, double *d_out, cudaStream_t st, int *launches);
+int sample_device(kdeb200_tree_t bd, int64_t Np, uint64_t seed, const double *d_randU, const double *d_randN,
+                  double *d_points, int64_t *d_idx, cudaStream_t st, int *launches);
 void set_prune_mode(int m);
 int get_prune_mode();
 int pruned_last_stats(double *kept_fraction, int64_t *redo_rows);
@@ -482,6 +485,62 @@ int kdeb200_kde_lcv_sharded(int d, int64_t N, const double *points, int64_t j0, 
   if (!points || !bw_std_out || !allreduce) KDE_FAIL(2, "kde_lcv_sharded: NULL argument");
   ScalarExchange x{allreduce, user};
   return kde_lcv(d, N, points, j0, j1, scalar_exchange_adapter, &x, bw_std_out, nloo_calls_out);
+}
+
+int kdeb200_eval_marginals(kdeb200_tree_t bd, const double *grids, int64_t G, double *out) {
+  KDE_SERIALISE();
+  if (int rc = ensure_init()) return rc;
+  if (!bd || !grids || !out) KDE_FAIL(2, "eval_marginals: NULL argument");
+  if (G <= 0) return 0;
+  Context &c = ctx();
+  DevBuf dG(c.stream), dO(c.stream);
+  const size_t bytes = sizeof(double) * (size_t)bd->d * G;
+  KDE_CUDA(dG.alloc(bytes));
+  KDE_CUDA(dO.alloc(bytes));
+  KDE_CUDA(cudaMemcpyAsync(dG.p, grids, bytes, cudaMemcpyHostToDevice, c.stream));
+  Timer tm(c);
+  int launches = 0;
+  if (int rc = eval_marginals_device(bd, dG.as<double>(), G, dO.as<double>(), c.stream, &launches)) return rc;
+  tm.stop();
+  c.last_launches = launches;
+  KDE_CUDA(cudaMemcpyAsync(out, dO.p, bytes, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int kdeb200_sample(kdeb200_tree_t bd, int64_t Np, uint64_t seed, const double *randU, const double *randN,
+                   double *points_out, int64_t *ind_out) {
+  KDE_SERIALISE();
+  if (int rc = ensure_init()) return rc;
+  if (!bd || !points_out || !ind_out) KDE_FAIL(2, "sample: NULL argument");
+  if (Np < 0 || Np >= ((int64_t)1 << 31)) KDE_FAIL(3, "sample: Np out of range");
+  if (Np == 0) return 0;
+  for (int k = 0; k < bd->d; ++k)
+    if (!(bd->hvar[k] >= 0.0)) KDE_FAIL(5, "sample: negative bandwidth variance");
+  Context &c = ctx();
+  const int d = bd->d;
+  DevBuf dU(c.stream), dN(c.stream), dP(c.stream), dI(c.stream);
+  if (randU) {
+    KDE_CUDA(dU.alloc(sizeof(double) * Np));
+    KDE_CUDA(cudaMemcpyAsync(dU.p, randU, sizeof(double) * Np, cudaMemcpyHostToDevice, c.stream));
+  }
+  if (randN) {
+    KDE_CUDA(dN.alloc(sizeof(double) * d * Np));
+    KDE_CUDA(cudaMemcpyAsync(dN.p, randN, sizeof(double) * d * Np, cudaMemcpyHostToDevice, c.stream));
+  }
+  KDE_CUDA(dP.alloc(sizeof(double) * d * Np));
+  KDE_CUDA(dI.alloc(sizeof(int64_t) * Np));
+  Timer tm(c);
+  int launches = 0;
+  if (int rc = sample_device(bd, Np, seed, randU ? dU.as<double>() : nullptr, randN ? dN.as<double>() : nullptr,
+                             dP.as<double>(), dI.as<int64_t>(), c.stream, &launches))
+    return rc;
+  tm.stop();
+  c.last_launches = launches;
+  KDE_CUDA(cudaMemcpyAsync(points_out, dP.p, sizeof(double) * d * Np, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaMemcpyAsync(ind_out, dI.p, sizeof(int64_t) * Np, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
 }
 
 int kdeb200_set_pruning(int mode) {

@@ -311,14 +311,16 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
     P.labels[j] = t->d_labels;
     for (int k = 0; k < d; ++k) P.hvar[j][k] = t->hvar[k];
   }
-  // Few chains: one warp per chain (K1w).  The thread-per-chain kernel needs ~128 x 4 x SMs chains to fill the chip;
-  // below ~96 chains per SM the warp kernel finishes sooner (KDEB200_GIBBS_WARP_MAX overrides; 0 disables it).  Its
-  // prefix sums live in shared memory, which bounds the level size.
+  // Few chains: one warp per chain (K1w).  The thread-per-chain kernel needs ~128 x 4 x SMs chains to fill the chip and
+  // costs the same 0.3 - 3 ms whether it runs 100 chains or 10 000; measured crossover (tools/gibbs_kernel_crossover.py,
+  // profiles/r02_gibbs_crossover.json): ~4 000 chains for 2 - 6 densities of 100 - 1000 components, so the warp
+  // kernel takes calls of up to 24 chains per SM (KDEB200_GIBBS_WARP_MAX overrides; 0 disables it).  Its prefix sums
+  // live in shared memory, which bounds the level size.
   {
     int nmax = 1;
     for (int j = 0; j < ndens; ++j)
       if (trees[j]->levels[trees[j]->depth].n > nmax) nmax = (int)trees[j]->levels[trees[j]->depth].n;
-    int64_t warp_max = (int64_t)96 * c.sm_count;
+    int64_t warp_max = (int64_t)24 * c.sm_count;
     if (const char *ev = getenv("KDEB200_GIBBS_WARP_MAX")) warp_max = atoll(ev);
     if (s1 - s0 <= warp_max && gibbs_warp_smem(d, nmax) <= 96 * 1024) {
       cudaError_t we = cudaErrorInvalidValue;

@@ -132,15 +132,27 @@ __device__ __forceinline__ void load_rec(const double *__restrict__ r, double (&
   }
 }
 
+// the same through the read-only path (LDG.NC, L1-cached): GLOBAL pointers only -- the warp-per-chain kernel, whose
+// four chains per CTA and T + 1 passes per level re-read the same records
+template <int S>
+__device__ __forceinline__ void load_rec_nc(const double *__restrict__ r, double (&rr)[S]) {
+#pragma unroll
+  for (int k = 0; k < S; k += 2) {
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(r + k));
+    rr[k] = v.x;
+    rr[k + 1] = v.y;
+  }
+}
+
 // One evaluation is split in two stages so that pass 1 can software-pipeline them (stage 1 of
 // node group g overlaps the exp chains of group g-1 in one basic block):
 //   pre_*: record -> exponent argument (and, variant C, the normaliser rsqrt(prod c_k))
 //   fin  : p = exp(arg) [* scale]
-template <int D, bool MASK>
+template <int D, bool MASK, bool NC = false>
 __device__ __forceinline__ void pre_A(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg, double &sc) {
   constexpr int S = (D + 2) & ~1;
   double rr[S];
-  load_rec<S>(r, rr);
+  if (NC) load_rec_nc<S>(r, rr); else load_rec<S>(r, rr);
   double acc = rr[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) {
@@ -153,11 +165,11 @@ __device__ __forceinline__ void pre_A(const double *__restrict__ r, const Hoist<
   sc = 1.0;
 }
 
-template <int D, bool MASK>
+template <int D, bool MASK, bool NC = false>
 __device__ __forceinline__ void pre_B(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg, double &sc) {
   constexpr int S = (2 * D + 2) & ~1;
   double rr[S];
-  load_rec<S>(r, rr);
+  if (NC) load_rec_nc<S>(r, rr); else load_rec<S>(r, rr);
   double acc = rr[2 * D];
 #pragma unroll
   for (int k = 0; k < D; ++k) {
@@ -168,11 +180,11 @@ __device__ __forceinline__ void pre_B(const double *__restrict__ r, const Hoist<
   sc = 1.0;
 }
 
-template <int D, bool MASK>
+template <int D, bool MASK, bool NC = false>
 __device__ __forceinline__ void pre_C(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg, double &sc) {
   constexpr int S = (2 * D + 2) & ~1;
   double rr[S];
-  load_rec<S>(r, rr);
+  if (NC) load_rec_nc<S>(r, rr); else load_rec<S>(r, rr);
   if (D == 3 && !MASK) {
     // one MUFU.RSQ64H for the normaliser AND the three reciprocals:
     //   rs = rsqrt(c0 c1 c2), R = rs^2 = 1/(c0 c1 c2), 1/c_k = R * prod_{i != k} c_i   (38 FP64 instr / node)
@@ -240,12 +252,12 @@ __device__ __forceinline__ void pre_C(const double *__restrict__ r, const Hoist<
   sc = kde_rsqrt(prod);
 }
 
-template <int D, bool MASK, int VAR>
+template <int D, bool MASK, int VAR, bool NC = false>
 __device__ __forceinline__ void pre_node(const double *__restrict__ r, const Hoist<D, MASK> &h, double &arg,
                                          double &sc) {
-  if (VAR == VAR_A) pre_A<D, MASK>(r, h, arg, sc);
-  else if (VAR == VAR_B) pre_B<D, MASK>(r, h, arg, sc);
-  else pre_C<D, MASK>(r, h, arg, sc);
+  if (VAR == VAR_A) pre_A<D, MASK, NC>(r, h, arg, sc);
+  else if (VAR == VAR_B) pre_B<D, MASK, NC>(r, h, arg, sc);
+  else pre_C<D, MASK, NC>(r, h, arg, sc);
 }
 
 template <int VAR>
@@ -254,11 +266,11 @@ __device__ __forceinline__ double fin_node(double arg, double sc, const double *
   return (VAR == VAR_C) ? __dmul_rn(e, sc) : e;
 }
 
-template <int D, bool MASK, int VAR>
+template <int D, bool MASK, int VAR, bool NC = false>
 __device__ __forceinline__ double eval_node(const double *__restrict__ r, const Hoist<D, MASK> &h,
                                             const double *__restrict__ tab, const ExpConsts &ec) {
   double arg, sc;
-  pre_node<D, MASK, VAR>(r, h, arg, sc);
+  pre_node<D, MASK, VAR, NC>(r, h, arg, sc);
   return fin_node<VAR>(arg, sc, tab, ec);
 }
 
@@ -695,8 +707,10 @@ __global__ void __launch_bounds__(GW_WARPS * 32) gibbs_warp_kernel(const __grid_
   if (lane < M) selpos[lane] = 0;
   __syncwarp();
 
+  Draw dr_next = P.draws[0];
   for (int di = 0; di < P.ndraws; ++di) {
-    const Draw dr = P.draws[di];
+    const Draw dr = dr_next;
+    if (di + 1 < P.ndraws) dr_next = P.draws[di + 1];  // in flight while this draw computes
     const int j = dr.j;
     if (dr.new_level) {  // samplePoint!(addEntropy = true): lane k owns dimension k
       if (lane < D) {
@@ -770,9 +784,9 @@ __global__ void __launch_bounds__(GW_WARPS * 32) gibbs_warp_kernel(const __grid_
     for (int z = lane; z < n; z += 32) {
       const double *r = dr.rec + (size_t)z * dr.stride;
       double p;
-      if (dr.variant == VAR_A) p = eval_node<D, MASK, VAR_A>(r, h, tab, P.ec);
-      else if (dr.variant == VAR_B) p = eval_node<D, MASK, VAR_B>(r, h, tab, P.ec);
-      else p = eval_node<D, MASK, VAR_C>(r, h, tab, P.ec);
+      if (dr.variant == VAR_A) p = eval_node<D, MASK, VAR_A, true>(r, h, tab, P.ec);
+      else if (dr.variant == VAR_B) p = eval_node<D, MASK, VAR_B, true>(r, h, tab, P.ec);
+      else p = eval_node<D, MASK, VAR_C, true>(r, h, tab, P.ec);
       pbuf[z] = p;
     }
     __syncwarp();
@@ -843,10 +857,10 @@ __global__ void __launch_bounds__(GW_WARPS * 32) gibbs_warp_kernel(const __grid_
         lam[j * D + k] = 0.0;
         lmu[j * D + k] = 0.0;
       } else {
-        const double var = dr.state_has_bw ? rs[D + k] : P.hvar[j][k];
+        const double var = dr.state_has_bw ? __ldg(rs + D + k) : P.hvar[j][k];
         const double l = 1.0 / var;
         lam[j * D + k] = l;
-        lmu[j * D + k] = rs[k] * l;
+        lmu[j * D + k] = __ldg(rs + k) * l;
       }
     }
     __syncwarp();

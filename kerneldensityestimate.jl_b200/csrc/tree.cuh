@@ -42,6 +42,8 @@ struct kdeb200_tree_s {
   float *d_leaf32 = nullptr;    // lazily built FP32 shadow of d_leaf (centred, pre-scaled), eval_f32.cu
   double *d_tilebox = nullptr;  // lazily built bounding boxes + weight sums of the component tiles (eval_pruned.cu)
   double wtotal = 0.0;          // sum_i |w_i| (error bound of the pruned evaluation)
+  double *d_cw = nullptr;       // lazily built: normalised cumulative weights in ORIGINAL point order (sample, extras.cu)
+  int64_t *d_leaf_of = nullptr; // ... and original index -> leaf position (same allocation as d_cw)
   size_t device_bytes = 0;
   int slot = 0;                 // context slot that owns the device memory (0 = primary)
   std::vector<int64_t> h_perm;  // host copy of d_perm (scatter of sharded LOO rows)

@@ -11,6 +11,24 @@ from tests import test_oracle_stats as STATS
 from tests.util import mixture, silverman
 
 pytestmark = pytest.mark.gpu
+
+# Both Gibbs kernels must pass everything: "thread" = one thread per chain (K1, the throughput kernel), "warp" = one warp
+# per chain (K1w, the small-call kernel).  The library picks by the number of chains; KDEB200_GIBBS_WARP_MAX overrides.
+HEAVY = ("test_full_size_c4_properties", "test_very_large_trees_multi_tile_chunks", "test_large_trees_c4_shape")
+
+
+@pytest.fixture(autouse=True, params=["thread", "warp"])
+def gibbs_kernel_choice(request):
+    import os
+    if request.param == "warp" and request.node.name.split("[")[0] in HEAVY:
+        pytest.skip("sized for the thread-per-chain kernel (level lists beyond the warp kernel's shared memory, or 1M chains)")
+    old = os.environ.get("KDEB200_GIBBS_WARP_MAX")
+    os.environ["KDEB200_GIBBS_WARP_MAX"] = "0" if request.param == "thread" else "1000000000"
+    yield request.param
+    if old is None:
+        os.environ.pop("KDEB200_GIBBS_WARP_MAX", None)
+    else:
+        os.environ["KDEB200_GIBBS_WARP_MAX"] = old
 PT_TOL = 1e-10
 
 
