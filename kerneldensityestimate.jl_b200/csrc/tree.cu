@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <algorithm>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -23,36 +24,161 @@ namespace kdeb200 {
 
 namespace {
 
+constexpr int KDEB200_MAX_DIM_HOST = 64;  // the host builder serves any d the reference accepts (the device path: <= 8)
+
+inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// runs fn(begin, end) over [0, n) on up to `threads` host threads (first-touch page faults and gathers of big trees)
+template <class F>
+void parallel_ranges(int64_t n, int threads, F fn) {
+  if (threads <= 1 || n < 65536) {
+    fn((int64_t)0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int64_t per = (n + threads - 1) / threads;
+  for (int t = 1; t < threads; ++t) {
+    const int64_t a = t * per, b = (a + per < n) ? a + per : n;
+    if (a < b) th.emplace_back([=] { fn(a, b); });
+  }
+  fn((int64_t)0, per < n ? per : n);
+  for (auto &x : th) x.join();
+}
+
 struct Builder {
   int d;
   int64_t N;
   const double *pts;          // d x N, original order
+  const double *wts_in, *bw_var;
   std::vector<int64_t> ord;   // leaf slot -> original index
-  int64_t *left, *right, *lowest, *highest;
+  std::vector<double> s_key, s_kq;  // scratch of nth(), indexed by slot
+  std::vector<int64_t> s_oq;
+  double *centers, *ranges, *wout, *means, *bandwidth;
+  int64_t *left, *right, *lowest, *highest, *perm;
 
   inline double key(int64_t slot, int dim) const { return pts[ord[slot] * d + dim]; }
 
-  int spread_dim(int64_t lo, int64_t hi) const {  // slots lo..hi-1 (the last leaf is excluded, as in the reference)
-    double best = 0.0;
-    int arg = 0;
+  // most_spread_coord (src/BallTree01.jl:142-173): slots lo..hi-1 (the last leaf is excluded, as in the reference).
+  // The sums keep the reference's order (sequential per dimension), but all d dimensions share ONE pass over the points
+  // for the means and one for the variances -- a point's coordinates sit in one cache line, and the 2 d separate passes
+  // of the literal form were the cache misses that dominated the top of the tree.
+  int spread_dim(int64_t lo, int64_t hi) const {
     const double w = 1.0 / (double)(hi - lo);
-    for (int k = 0; k < d; ++k) {
-      double mean = 0.0;
-      for (int64_t s = lo; s < hi; ++s) mean = mean + w * key(s, k);
-      double var = 0.0;
-      for (int64_t s = lo; s < hi; ++s) {
-        const double df = key(s, k) - mean;
-        var += df * df;
-      }
-      if (var > best) {
-        best = var;
-        arg = k;
+    double mean[KDEB200_MAX_DIM_HOST], var[KDEB200_MAX_DIM_HOST];
+    for (int k = 0; k < d; ++k) mean[k] = var[k] = 0.0;
+    for (int64_t s = lo; s < hi; ++s) {
+      const double *x = pts + ord[s] * d;
+      for (int k = 0; k < d; ++k) mean[k] = mean[k] + w * x[k];
+    }
+    for (int64_t s = lo; s < hi; ++s) {
+      const double *x = pts + ord[s] * d;
+      for (int k = 0; k < d; ++k) {
+        const double df = x[k] - mean[k];
+        var[k] += df * df;
       }
     }
+    double best = 0.0;
+    int arg = 0;
+    for (int k = 0; k < d; ++k)
+      if (var[k] > best) {
+        best = var[k];
+        arg = k;
+      }
     return arg;
   }
 
-  void nth(int dim, int64_t pos, int64_t lo, int64_t hi) {  // the reference's quick-select, swap for swap
+  // The reference's quick-select (select!, src/BallTree01.jl:223-242) -- same result, element for element, without its
+  // memory behaviour.  One pass of select! over slots [lo, hi] with the pivot in slot lo is a Lomuto partition:
+  //   m = lo; for i in lo..hi: if key(i) - key(lo) < 0 { ++m; swap(m, i) };  swap(lo, m)
+  // Slots lo+1..m collect the "less" elements in the order they are met; slots m+1..i-1 hold the others as a QUEUE:
+  // every less element that arrives sends the queue's front to its back (the swap), every other element joins the back.
+  // So the pass is reproduced by streaming the keys once (contiguous copies of the keys of this dimension, no indirect
+  // loads), settling the less elements in place and running the queue in a ring buffer -- branch-free, the comparison is
+  // a coin flip -- and writing the queue back behind the pivot: L_c, L_1..L_{c-1}, pivot, queue (the final swap moves
+  // the last less element to the front and the pivot behind the less block).
+  void nth(int dim, int64_t pos, int64_t lo, int64_t hi) {
+    const int64_t n0 = hi - lo + 1;
+    if (n0 < 2) return;
+    if (n0 < 48) {  // tiny ranges: the literal in-place form is cheapest
+      nth_inplace(dim, pos, lo, hi);
+      return;
+    }
+    // scratch indexed by slot: concurrent subtrees own disjoint slot ranges, so one set of arrays serves all threads
+    double *K = s_key.data(), *kq = s_kq.data() + lo;
+    int64_t *oq = s_oq.data() + lo;
+    for (int64_t i = lo; i <= hi; ++i) K[i] = pts[ord[i] * d + dim];
+    while (lo < hi) {
+      const int64_t n = hi - lo + 1;
+      if (n < 48) {
+        nth_inplace_keys(K, pos, lo, hi);
+        return;
+      }
+      const int64_t r = (lo + hi) / 2;
+      std::swap(ord[r], ord[lo]);
+      std::swap(K[r], K[lo]);
+      const double pk = K[lo];
+      const int64_t po = ord[lo];
+      int64_t c = 0, qh = 0, qn = 0;  // less count; queue head / size in a ring of capacity n (the queue holds <= n - 1)
+      const int64_t cap = n;
+      int64_t *O = ord.data();
+      for (int64_t i = lo + 1; i <= hi; ++i) {  // i = lo is the pivot itself: pk - pk < 0 is false and m stays lo
+        const double kv = K[i];
+        const int64_t ov = O[i];
+        const int64_t less = (kv - pk < 0.0) ? 1 : 0;
+        K[lo + 1 + c] = kv;  // less elements settle in place, in the order they are met (lo + 1 + c <= i: already read);
+        O[lo + 1 + c] = ov;  // the slot is simply rewritten by the next candidate when this one is not less
+        c += less;
+        int64_t tail = qh + qn;
+        tail -= (tail >= cap) ? cap : 0;
+        // less: the front goes to the back (a no-op write into a free slot while the queue is empty); else: append
+        kq[tail] = less ? kq[qh] : kv;
+        oq[tail] = less ? oq[qh] : ov;
+        const int64_t adv = less & (qn > 0 ? 1 : 0);
+        qh += adv;
+        qh -= (qh >= cap) ? cap : 0;
+        qn += 1 - less;
+      }
+      const int64_t m = lo + c;
+      if (c > 0) {  // the final swap(lo, m): the last less element to the front, the pivot behind the less block
+        K[lo] = K[m];
+        O[lo] = O[m];
+      }
+      K[m] = pk;
+      O[m] = po;
+      const int64_t first = (qn < cap - qh) ? qn : cap - qh;  // the ring in at most two pieces
+      std::memcpy(K + m + 1, kq + qh, sizeof(double) * (size_t)first);
+      std::memcpy(O + m + 1, oq + qh, sizeof(int64_t) * (size_t)first);
+      std::memcpy(K + m + 1 + first, kq, sizeof(double) * (size_t)(qn - first));
+      std::memcpy(O + m + 1 + first, oq, sizeof(int64_t) * (size_t)(qn - first));
+      if (m <= pos) lo = m + 1;
+      if (m >= pos) hi = m - 1;
+    }
+  }
+
+  void nth_inplace_keys(double *K, int64_t pos, int64_t lo, int64_t hi) {  // select! on the contiguous keys
+    while (lo < hi) {
+      const int64_t r = (lo + hi) / 2;
+      std::swap(ord[r], ord[lo]);
+      std::swap(K[r], K[lo]);
+      int64_t m = lo;
+      const int64_t l0 = lo, h0 = hi;
+      for (int64_t i = l0; i <= h0; ++i) {
+        if (K[i] - K[l0] < 0.0) {
+          ++m;
+          std::swap(ord[m], ord[i]);
+          std::swap(K[m], K[i]);
+        }
+      }
+      std::swap(ord[lo], ord[m]);
+      std::swap(K[lo], K[m]);
+      if (m <= pos) lo = m + 1;
+      if (m >= pos) hi = m - 1;
+    }
+  }
+
+  void nth_inplace(int dim, int64_t pos, int64_t lo, int64_t hi) {  // the reference's quick-select, swap for swap
     while (lo < hi) {
       const int64_t r = (lo + hi) / 2;
       std::swap(ord[r], ord[lo]);
@@ -71,96 +197,24 @@ struct Builder {
     }
   }
 
-  // node ids are the reference's 1-based ids; slots are 0-based leaf positions (node = N+1+slot).
-  // The reference hands out internal ids from a running counter in depth-first order (src/BallTree01.jl:415-434);
-  // a subtree over n >= 2 leaves consumes exactly n - 2 of them below its root, so the first free id of every
-  // subtree is known up front (next0) and disjoint subtrees can be built by different host threads.
-  // post: internal nodes in calcStats order (children before parents).
-  void topo(int64_t lo, int64_t hi, int64_t root, int64_t next0, std::vector<int64_t> &post, int par_depth) {
-    const int64_t nlo = N + 1 + lo, nhi = N + 1 + hi;
-    if (lo == hi) {  // single-point tree
-      lowest[root - 1] = nlo;
-      highest[root - 1] = nhi;
-      left[root - 1] = nlo;
-      right[root - 1] = -1;
-      post.push_back(-root);  // negative: "left child counted once" special case
-      return;
-    }
-    const int dim = spread_dim(lo, hi);
-    const int64_t split = (lo + hi) / 2;
-    nth(dim, split, lo, hi);
-    int64_t l, r, nxt = next0;
-    if (split <= lo) l = nlo; else l = nxt++;
-    if (split + 1 >= hi) r = nhi; else r = nxt++;
-    lowest[root - 1] = nlo;
-    highest[root - 1] = nhi;
-    left[root - 1] = l;
-    right[root - 1] = r;
-    const int64_t nleft = split - lo + 1;
-    const int64_t next_right = nxt + (nleft >= 2 ? nleft - 2 : 0);
-    if (par_depth > 0 && hi - lo + 1 >= 32768 && l != nlo && r != nhi) {
-      std::vector<int64_t> post_left;
-      post_left.reserve((size_t)nleft);
-      std::thread th([&] { topo(lo, split, l, nxt, post_left, par_depth - 1); });
-      std::vector<int64_t> post_right;
-      post_right.reserve((size_t)(hi - split));
-      topo(split + 1, hi, r, next_right, post_right, par_depth - 1);
-      th.join();
-      post.insert(post.end(), post_left.begin(), post_left.end());
-      post.insert(post.end(), post_right.begin(), post_right.end());
-    } else {
-      if (l != nlo) topo(lo, split, l, nxt, post, 0);
-      if (r != nhi) topo(split + 1, hi, r, next_right, post, 0);
-    }
-    post.push_back(root);
-  }
-};
-
-}  // namespace
-
-int tree_build_host(int d, int64_t N, const double *points, const double *weights, const double *bw_var,
-                    double *centers, double *ranges, double *wout, double *means, double *bandwidth,
-                    int64_t *left, int64_t *right, int64_t *lowest, int64_t *highest, int64_t *perm) {
-  if (d < 1 || N < 1) KDE_FAIL(2, "tree_build: need d >= 1 and N >= 1 (got d=%d N=%lld)", d, (long long)N);
-  const int64_t NN = 2 * N;
-  std::memset(centers, 0, sizeof(double) * NN * d);
-  std::memset(ranges, 0, sizeof(double) * NN * d);
-  std::memset(means, 0, sizeof(double) * NN * d);
-  std::memset(bandwidth, 0, sizeof(double) * NN * d);
-  std::memset(wout, 0, sizeof(double) * NN);
-  for (int64_t i = 0; i < NN; ++i) {
-    left[i] = right[i] = lowest[i] = highest[i] = 1;  // ones(Int, 2Np)
-    perm[i] = 0;
-  }
-  Builder b;
-  b.d = d; b.N = N; b.pts = points;
-  b.left = left; b.right = right; b.lowest = lowest; b.highest = highest;
-  b.ord.resize(N);
-  for (int64_t i = 0; i < N; ++i) b.ord[i] = i;
-  for (int64_t i = N; i < NN; ++i) {  // leaves
-    lowest[i] = highest[i] = left[i] = i + 1;
-    right[i] = -1;
-  }
-  std::vector<int64_t> post;
-  post.reserve(N);
-  int par_depth = 4;  // up to 16 host threads on large inputs; KDEB200_BUILD_PAR_DEPTH=0 builds on the calling thread
-  if (const char *e = getenv("KDEB200_BUILD_PAR_DEPTH")) par_depth = atoi(e);
-  b.topo(0, N - 1, 1, 2, post, par_depth);
-
-  for (int64_t s = 0; s < N; ++s) {  // gather the leaf payload once
-    const int64_t o = b.ord[s], node = N + s;
+  // leaf payload of slot s (its final occupant is known once the recursion reaches it)
+  inline void gather_leaf(int64_t s) {
+    const int64_t o = ord[s], node = N + s;
     perm[node] = o + 1;
-    wout[node] = weights[o];
+    wout[node] = wts_in[o];
     for (int k = 0; k < d; ++k) {
-      centers[node * d + k] = points[o * d + k];
-      means[node * d + k] = points[o * d + k];
+      centers[node * d + k] = pts[o * d + k];
+      means[node * d + k] = pts[o * d + k];
       bandwidth[node * d + k] = bw_var[k];
+      ranges[node * d + k] = 0.0;
     }
   }
-  for (int64_t e : post) {  // node statistics, children before parents
-    const int64_t root = e < 0 ? -e : e;
+
+  // calcStatsBall! + calcStatsDensity! of one internal node, children done (src/BallTree01.jl:282-336,
+  // src/BallTreeDensity01.jl:141-187); single: the one-point tree, whose only child is counted once
+  inline void stats(int64_t root, bool single) {
     const int64_t L = left[root - 1];
-    const int64_t R = e < 0 ? L : right[root - 1];  // N == 1: right temporarily aliases left
+    const int64_t R = single ? L : right[root - 1];
     double *c = centers + (root - 1) * d, *rg = ranges + (root - 1) * d;
     const double *cl = centers + (L - 1) * d, *cr = centers + (R - 1) * d;
     const double *rl = ranges + (L - 1) * d, *rr = ranges + (R - 1) * d;
@@ -187,6 +241,96 @@ int tree_build_host(int d, int64_t N, const double *points, const double *weight
       bwd[k] = wl * (bl[k] + ml[k] * ml[k]) + wr * (br[k] + mr[k] * mr[k]) - mk * mk;
     }
   }
+
+  // node ids are the reference's 1-based ids; slots are 0-based leaf positions (node = N+1+slot).
+  // The reference hands out internal ids from a running counter in depth-first order (src/BallTree01.jl:415-434);
+  // a subtree over n >= 2 leaves consumes exactly n - 2 of them below its root, so the first free id of every
+  // subtree is known up front (next0) and disjoint subtrees can be built by different host threads -- topology, leaf
+  // payload and node statistics (children before parents) all inside the same recursion.
+  void topo(int64_t lo, int64_t hi, int64_t root, int64_t next0, int par_depth) {
+    const int64_t nlo = N + 1 + lo, nhi = N + 1 + hi;
+    if (lo == hi) {  // single-point tree
+      lowest[root - 1] = nlo;
+      highest[root - 1] = nhi;
+      left[root - 1] = nlo;
+      right[root - 1] = -1;
+      gather_leaf(lo);
+      stats(root, true);
+      return;
+    }
+    const bool tr = (hi - lo + 1 >= 400000) && getenv("KDEB200_TRACE") != nullptr;
+    const double t0 = tr ? now_ms() : 0.0;
+    const int dim = spread_dim(lo, hi);
+    const double t1 = tr ? now_ms() : 0.0;
+    const int64_t split = (lo + hi) / 2;
+    nth(dim, split, lo, hi);
+    if (tr) fprintf(stderr, "[kdeb200]   node of %lld leaves: spread %.1f ms, select %.1f ms\n", (long long)(hi - lo + 1), t1 - t0, now_ms() - t1);
+    int64_t l, r, nxt = next0;
+    if (split <= lo) l = nlo; else l = nxt++;
+    if (split + 1 >= hi) r = nhi; else r = nxt++;
+    lowest[root - 1] = nlo;
+    highest[root - 1] = nhi;
+    left[root - 1] = l;
+    right[root - 1] = r;
+    const int64_t nleft = split - lo + 1;
+    const int64_t next_right = nxt + (nleft >= 2 ? nleft - 2 : 0);
+    if (par_depth > 0 && hi - lo + 1 >= 32768 && l != nlo && r != nhi) {
+      std::thread th([&] { topo(lo, split, l, nxt, par_depth - 1); });
+      topo(split + 1, hi, r, next_right, par_depth - 1);
+      th.join();
+    } else {
+      if (l != nlo) topo(lo, split, l, nxt, 0); else gather_leaf(lo);
+      if (r != nhi) topo(split + 1, hi, r, next_right, 0); else gather_leaf(hi);
+    }
+    stats(root, false);
+  }
+};
+
+}  // namespace
+
+int tree_build_host(int d, int64_t N, const double *points, const double *weights, const double *bw_var,
+                    double *centers, double *ranges, double *wout, double *means, double *bandwidth,
+                    int64_t *left, int64_t *right, int64_t *lowest, int64_t *highest, int64_t *perm) {
+  if (d < 1 || N < 1) KDE_FAIL(2, "tree_build: need d >= 1 and N >= 1 (got d=%d N=%lld)", d, (long long)N);
+  if (d > KDEB200_MAX_DIM_HOST) KDE_FAIL(3, "tree_build: d=%d above %d", d, KDEB200_MAX_DIM_HOST);
+  const int64_t NN = 2 * N;
+  const double t_0 = now_ms();
+  int par_depth = 4;  // up to 16 host threads on large inputs; KDEB200_BUILD_PAR_DEPTH=0 builds on the calling thread
+  if (const char *e = getenv("KDEB200_BUILD_PAR_DEPTH")) par_depth = atoi(e);
+  const int nthreads = par_depth > 0 ? (int)std::min<unsigned>(1u << par_depth, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  Builder b;
+  b.d = d; b.N = N; b.pts = points; b.wts_in = weights; b.bw_var = bw_var;
+  b.centers = centers; b.ranges = ranges; b.wout = wout; b.means = means; b.bandwidth = bandwidth;
+  b.left = left; b.right = right; b.lowest = lowest; b.highest = highest; b.perm = perm;
+  b.ord.resize(N);
+  if (N >= 48) {
+    b.s_key.resize(N); b.s_kq.resize(N);
+    b.s_oq.resize(N);
+  }
+  // Every entry of the outputs is written exactly once: internal nodes 1..N-1 and leaves N+1..2N by the recursion, the
+  // index arrays and the unused slot N here (the reference: zeros(...) / ones(Int, 2Np)).  The caller's arrays are
+  // usually fresh pages, so the first touch is spread over the threads.
+  parallel_ranges(N, nthreads, [&](int64_t a, int64_t e) {
+    for (int64_t i = a; i < e; ++i) {
+      b.ord[i] = i;
+      left[i] = right[i] = lowest[i] = highest[i] = 1;  // internal entries: overwritten for 1..N-1, slot N keeps ones
+      perm[i] = 0;
+      const int64_t j = N + i;  // leaves
+      lowest[j] = highest[j] = left[j] = j + 1;
+      right[j] = -1;
+    }
+  });
+  for (int k = 0; k < d; ++k) {
+    const int64_t u = (N - 1) * d + k;
+    centers[u] = ranges[u] = means[u] = bandwidth[u] = 0.0;
+  }
+  wout[N - 1] = 0.0;
+  const bool trace = getenv("KDEB200_TRACE") != nullptr;
+  const double t_a = now_ms();
+  b.topo(0, N - 1, 1, 2, par_depth);
+  if (trace)
+    fprintf(stderr, "[kdeb200] tree_build_host d=%d N=%lld: init %.1f ms, topology + payload + statistics %.1f ms\n", d, (long long)N,
+            t_a - t_0, now_ms() - t_a);
   return 0;
 }
 
