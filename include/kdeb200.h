@@ -113,6 +113,15 @@ int kdeb200_gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int
                          const uint8_t *dimmask, const double *d_randU, int64_t nU, const double *d_randN,
                          int64_t nN, uint64_t seed, int64_t s0, int64_t s1, double *d_points,
                          int64_t *d_indices, int64_t *d_level_labels, void *stream);
+/* `*` in one call (src/MSGibbs01.jl:707-726): Np product samples by prodAppxMSGibbsS (Philox(seed)) and, without the
+ * samples leaving the device, the LOOCV bandwidths of kde!(pGM) (src/KDE01.jl:13-23): for Np <= 512 the Gibbs kernel is
+ * followed by ONE kernel that sorts every coordinate, rebuilds the 1-D ball-tree statistics of ksize / neighborMinMax on
+ * chip and runs all golden-section searches (bit-identical to kdeb200_gibbs + kdeb200_kde_lcv); larger Np fall back to that
+ * two-step route inside the call.  The caller builds the product density as kde!(points_out, bw_std_out).
+ * indices_out (ndens x Np) and nloo_calls_out (d) may be NULL. */
+int kdeb200_product_kde(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
+                        const uint8_t *dimmask, uint64_t seed, double *points_out, int64_t *indices_out,
+                        double *bw_std_out, int *nloo_calls_out);
 /* glbs.Nlevels (src/MSGibbs01.jl:555-568) and the per-sample stream consumption. */
 int kdeb200_gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels,
                         int64_t *uniforms_per_sample, int64_t *normals_per_sample,

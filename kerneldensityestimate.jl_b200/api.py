@@ -691,9 +691,18 @@ def prod(trees, glbs=None, addEntropy=True, seed=None, recordLabels=False):
     for p in trees:
         if d != Ndim(p):
             raise KDEError("kdes must have same dimension")
-    res = prodAppxMSGibbsS(None, trees, None, None, Niter=5, addEntropy=addEntropy, Np=numpts, seed=seed,
-                           recordLabels=recordLabels)
-    return (kde(res[0]), res[2]) if recordLabels else kde(res[0])
+    if recordLabels or numpts < 2:
+        res = prodAppxMSGibbsS(None, trees, None, None, Niter=5, addEntropy=addEntropy, Np=numpts, seed=seed,
+                               recordLabels=recordLabels)
+        return (kde(res[0]), res[2]) if recordLabels else kde(res[0])
+    # Gibbs + the LOOCV refit kde!(pGM) in ONE library call; up to 512 samples never leave the device in between
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    pts = np.zeros((numpts, d))
+    bw = np.zeros(d)
+    check(lib().kdeb200_product_kde(_handles(trees), len(trees), numpts, 5, int(bool(addEntropy)), None,
+                                    int(seed) & 0xFFFFFFFFFFFFFFFF, fptr(pts), None, fptr(bw), None))
+    return kde(pts.T, bw)
 
 
 # ------------------------------------------------------------------------- measurement -------

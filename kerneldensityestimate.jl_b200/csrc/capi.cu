@@ -22,6 +22,8 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
             double *bw_std_out, int *ncalls_out);
 int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int64_t q0, bool scatter,
                 const double *bw_var, double *d_out, cudaStream_t st, int *launches, int prune);
+int kde_lcv_points_device(int d, int64_t N, const double *d_points, double *d_out5, cudaStream_t st);
+void lcv_points_finish(int d, const double *out5, double *bw_std_out, int *ncalls_out);
 int eval_marginals_device(kdeb200_tree_t bd, const double *d_grid, int64_t G, double *d_out, cudaStream_t st, int *launches);
 int sample_device(kdeb200_tree_t bd, int64_t Np, uint64_t seed, const double *d_randU, const double *d_randN,
                   double *d_points, int64_t *d_idx, cudaStream_t st, int *launches);
@@ -485,6 +487,52 @@ int kdeb200_kde_lcv_sharded(int d, int64_t N, const double *points, int64_t j0, 
   if (!points || !bw_std_out || !allreduce) KDE_FAIL(2, "kde_lcv_sharded: NULL argument");
   ScalarExchange x{allreduce, user};
   return kde_lcv(d, N, points, j0, j1, scalar_exchange_adapter, &x, bw_std_out, nloo_calls_out);
+}
+
+int kdeb200_product_kde(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
+                        const uint8_t *dimmask, uint64_t seed, double *points_out, int64_t *indices_out,
+                        double *bw_std_out, int *nloo_calls_out) {
+  KDE_SERIALISE();
+  if (int rc = ensure_init()) return rc;
+  if (!trees || !points_out || !bw_std_out) KDE_FAIL(2, "product_kde: NULL argument");
+  if (Np < 2) KDE_FAIL(3, "product_kde: at least two product samples are needed for cross validation");
+  int L;
+  int64_t perU, perN;
+  if (int rc = gibbs_sizes(trees, ndens, Niter, &L, &perU, &perN, nullptr)) return rc;
+  ScopedDevice sd(0);
+  Context &c = ctx();
+  const int d = trees[0]->d;
+  DevBuf dP(c.stream), dI(c.stream), dO(c.stream);
+  KDE_CUDA(dP.alloc(sizeof(double) * d * Np));
+  KDE_CUDA(dI.alloc(sizeof(int64_t) * ndens * Np));
+  KDE_CUDA(dO.alloc(sizeof(double) * 5 * d));
+  Timer tm(c);
+  int launches = 0;
+  if (int rc = gibbs_device(trees, ndens, Np, Niter, add_entropy, dimmask, nullptr, 0, nullptr, 0, seed, 0, Np,
+                            dP.as<double>(), dI.as<int64_t>(), nullptr, c.stream, &launches))
+    return rc;
+  const bool fused = Np <= 512;  // the samples never leave the device between the two kernels
+  if (fused) {
+    if (int rc = kde_lcv_points_device(d, Np, dP.as<double>(), dO.as<double>(), c.stream)) return rc;
+    ++launches;
+  }
+  tm.stop();
+  c.last_launches = launches;
+  double out5[5 * KDEB200_MAX_DIM];
+  KDE_CUDA(cudaMemcpyAsync(points_out, dP.p, sizeof(double) * d * Np, cudaMemcpyDeviceToHost, c.stream));
+  if (indices_out)
+    KDE_CUDA(cudaMemcpyAsync(indices_out, dI.p, sizeof(int64_t) * ndens * Np, cudaMemcpyDeviceToHost, c.stream));
+  if (fused) KDE_CUDA(cudaMemcpyAsync(out5, dO.p, sizeof(double) * 5 * d, cudaMemcpyDeviceToHost, c.stream));
+  KDE_CUDA(cudaStreamSynchronize(c.stream));
+  if (fused) {
+    lcv_points_finish(d, out5, bw_std_out, nloo_calls_out);
+    return 0;
+  }
+  // larger products: the bandwidth loop over the tiled LOO kernels (marginal trees on the host)
+  const double ms_gibbs = c.last_ms;
+  int rc = kde_lcv(d, Np, points_out, 0, Np, nullptr, nullptr, bw_std_out, nloo_calls_out);
+  c.last_ms += ms_gibbs;
+  return rc;
 }
 
 int kdeb200_eval_marginals(kdeb200_tree_t bd, const double *grids, int64_t G, double *out) {

@@ -85,6 +85,47 @@ __device__ __forceinline__ double lcv_nloo(double alpha, double &b, const double
   return H;
 }
 
+// golden (src/CrossValidation.jl:44-98), executed redundantly (and identically) by every thread of the CTA
+__device__ __forceinline__ void lcv_golden_run(const LcvDim D, const double *__restrict__ rec, int N, const double *__restrict__ tab,
+                                               const ExpConsts &ec, double norm0, double tol, double Cg, double Rg, double *sh,
+                                               int *shf, double *out3) {
+  double b = D.b0;
+  const double ax = D.ax, bx = 1.0, cx = D.cx;
+  double x0 = ax, x3 = cx, x1, x2;
+  if (fabs(cx - bx) > fabs(bx - ax)) {
+    x1 = bx;
+    x2 = __dadd_rn(bx, __dmul_rn(Cg, cx - bx));  // explicit roundings: no FMA contraction, like the host loop
+  } else {
+    x1 = __dadd_rn(bx, -__dmul_rn(Cg, bx - ax));
+    x2 = bx;
+  }
+  double f1 = lcv_nloo(x1, b, rec, N, tab, ec, norm0, sh, shf);
+  double f2 = lcv_nloo(x2, b, rec, N, tab, ec, norm0, sh, shf);
+  int n = 2;
+  while (fabs(x3 - x0) > tol * (fabs(x1) + fabs(x2))) {
+    if (f2 < f1) {
+      x0 = x1;
+      x1 = x2;
+      x2 = __dadd_rn(__dmul_rn(Rg, x1), __dmul_rn(Cg, x3));
+      f1 = f2;
+      f2 = lcv_nloo(x2, b, rec, N, tab, ec, norm0, sh, shf);
+    } else {
+      x3 = x2;
+      x2 = x1;
+      x1 = __dadd_rn(__dmul_rn(Rg, x2), __dmul_rn(Cg, x0));
+      f2 = f1;
+      f1 = lcv_nloo(x1, b, rec, N, tab, ec, norm0, sh, shf);
+    }
+    ++n;
+    if (n > 4096) break;  // NaN-proofing: the reference would spin forever
+  }
+  if (threadIdx.x == 0) {
+    out3[0] = (f1 < f2) ? x1 : x2;
+    out3[1] = (f1 < f2) ? f1 : f2;
+    out3[2] = (double)n;
+  }
+}
+
 __global__ void __launch_bounds__(LCV_THREADS) lcv_golden_kernel(const __grid_constant__ LcvParams P) {
   __shared__ __align__(16) double tab[KDE_EXP_TAB];
   __shared__ __align__(16) double rec[2 * LCV_FUSED_MAX];
@@ -94,43 +135,117 @@ __global__ void __launch_bounds__(LCV_THREADS) lcv_golden_kernel(const __grid_co
   for (int i = threadIdx.x; i < KDE_EXP_TAB; i += LCV_THREADS) tab[i] = P.exptab[i];
   for (int i = threadIdx.x; i < 2 * N; i += LCV_THREADS) rec[i] = P.leaf[(size_t)dim * 2 * N + i];
   __syncthreads();
+  lcv_golden_run(P.dims[dim], rec, N, tab, P.ec, P.norm0, P.tol, P.Cg, P.Rg, sh, shf, P.out + dim * 3);
+}
 
-  // golden (src/CrossValidation.jl:44-98), executed redundantly (and identically) by every thread
-  const LcvDim D = P.dims[dim];
-  double b = D.b0;
-  const double ax = D.ax, bx = 1.0, cx = D.cx, Cg = P.Cg, Rg = P.Rg;
-  double x0 = ax, x3 = cx, x1, x2;
-  if (fabs(cx - bx) > fabs(bx - ax)) {
-    x1 = bx;
-    x2 = __dadd_rn(bx, __dmul_rn(Cg, cx - bx));  // explicit roundings: no FMA contraction, like the host loop
-  } else {
-    x1 = __dadd_rn(bx, -__dmul_rn(Cg, bx - ax));
-    x2 = bx;
-  }
-  double f1 = lcv_nloo(x1, b, rec, N, tab, P.ec, P.norm0, sh, shf);
-  double f2 = lcv_nloo(x2, b, rec, N, tab, P.ec, P.norm0, sh, shf);
-  int n = 2;
-  while (fabs(x3 - x0) > P.tol * (fabs(x1) + fabs(x2))) {
-    if (f2 < f1) {
-      x0 = x1;
-      x1 = x2;
-      x2 = __dadd_rn(__dmul_rn(Rg, x1), __dmul_rn(Cg, x3));
-      f1 = f2;
-      f2 = lcv_nloo(x2, b, rec, N, tab, P.ec, P.norm0, sh, shf);
-    } else {
-      x3 = x2;
-      x2 = x1;
-      x1 = __dadd_rn(__dmul_rn(Rg, x2), __dmul_rn(Cg, x0));
-      f2 = f1;
-      f1 = lcv_nloo(x1, b, rec, N, tab, P.ec, P.norm0, sh, shf);
+// The same search on points that are ALREADY ON THE DEVICE (the product samples of `*`, src/MSGibbs01.jl:723-725:
+// kde!(pGM) right after the Gibbs kernel): the per-dimension 1-D ball tree of ksize is never built on
+// the host.  CTA `dim` sorts its coordinate in shared memory (in 1-D the tree's leaf order IS the sorted order; equal
+// points carry equal weights, so their mutual order cannot matter), rebuilds the node statistics the bracket needs --
+// centre and half-range of every node of the median-split tree, bottom-up with the reference's arithmetic
+// (calcStatsBall!, src/BallTree01.jl:282-336), laid out as an implicit heap -- takes neighborMinMax
+// (src/CrossValidation.jl:100-108) from them and runs the golden-section search above.  Bit-identical to the host route.
+struct LcvPointsParams {
+  const double *pts;  // N points, point i at pts + i * d
+  double *out;        // [dim][5]: xmin, fmin, number of nLOO_LL calls, minm, maxm
+  const double *exptab;
+  ExpConsts ec;
+  int N, d;
+  double w2;          // the (uniform) weight of the working density of ksize, renormalised twice like the host route
+  double norm0, tol, Cg, Rg;
+};
+
+__global__ void __launch_bounds__(LCV_THREADS) lcv_golden_points_kernel(const __grid_constant__ LcvPointsParams P) {
+  __shared__ __align__(16) double tab[KDE_EXP_TAB];  // prologue: the heap (centres | half-ranges), then the exp table
+  __shared__ __align__(16) double rec[2 * LCV_FUSED_MAX];
+  __shared__ double sh[LCV_THREADS];
+  __shared__ int shf[LCV_THREADS];
+  const int dim = blockIdx.x, N = P.N, tid = threadIdx.x;
+  // ---- sort (bitonic, 512 slots padded with +inf)
+  double *sb = sh;
+  if (tid < LCV_FUSED_MAX) sb[tid] = (tid < N) ? P.pts[(size_t)tid * P.d + dim] : INFINITY;
+  __syncthreads();
+  for (int k = 2; k <= LCV_FUSED_MAX; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (tid < LCV_FUSED_MAX) {
+        const int ixj = tid ^ j;
+        if (ixj > tid) {
+          const double a = sb[tid], c = sb[ixj];
+          const bool up = (tid & k) == 0;
+          if ((a > c) == up) {
+            sb[tid] = c;
+            sb[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
     }
-    ++n;
-    if (n > 4096) break;  // NaN-proofing: the reference would spin forever
+  // ---- node statistics on the implicit heap: node h covers the leaf interval reached from [0, N-1] by the bits of h
+  double *hc = tab, *hr = tab + 1024;
+  const int h = tid + 1;  // 1..1024; ids >= 1024 cannot exist for N <= 512
+  int lvl = 31 - __clz(h), lo = 0, hi = N - 1;
+  bool valid = h < 1024;
+  for (int bit = lvl - 1; bit >= 0 && valid; --bit) {
+    if (lo == hi) {
+      valid = false;
+      break;
+    }
+    const int split = (lo + hi) / 2;
+    if ((h >> bit) & 1) lo = split + 1; else hi = split;
   }
-  if (threadIdx.x == 0) {
-    P.out[dim * 3 + 0] = (f1 < f2) ? x1 : x2;
-    P.out[dim * 3 + 1] = (f1 < f2) ? f1 : f2;
-    P.out[dim * 3 + 2] = (double)n;
+  const bool internal = valid && lo < hi;
+  if (valid && lo == hi) {
+    hc[h] = sb[lo];
+    hr[h] = 0.0;
+  }
+  __syncthreads();
+  for (int depth = 9; depth >= 0; --depth) {
+    if (internal && lvl == depth) {
+      const double cl = hc[2 * h], rl = hr[2 * h], cr = hc[2 * h + 1], rr = hr[2 * h + 1];
+      const double hiL = __dadd_rn(cl, rl), hiR = __dadd_rn(cr, rr);
+      const double maxi = hiL > hiR ? hiL : hiR;
+      const double loL = __dadd_rn(cl, -rl), loR = __dadd_rn(cr, -rr);
+      const double mini = loL < loR ? loL : loR;
+      const double half = __ddiv_rn(__dadd_rn(maxi, -mini), 2.0);
+      hr[h] = half;
+      hc[h] = __dadd_rn(mini, half);
+    }
+    __syncthreads();
+  }
+  // ---- the working density's records, neighborMinMax, the bracket
+  for (int i = tid; i < N; i += LCV_THREADS) {
+    rec[2 * i] = sb[i];
+    rec[2 * i + 1] = P.w2;
+  }
+  double nrm = INFINITY;
+  if (internal) {
+    const double t = __dmul_rn(2.0, hr[h]);
+    nrm = __dsqrt_rn(__dmul_rn(t, t));
+  }
+  const double root_nrm = [&] {
+    const double t = __dmul_rn(2.0, hr[1]);
+    return __dsqrt_rn(__dmul_rn(t, t));
+  }();
+  __syncthreads();  // sb (= sh) has been copied out
+  sh[tid] = nrm;
+  __syncthreads();
+  for (int off = LCV_THREADS / 2; off > 0; off >>= 1) {
+    if (tid < off) sh[tid] = fmin(sh[tid], sh[tid + off]);
+    __syncthreads();
+  }
+  const double minm = fmax(sh[0], 1e-6), maxm = root_nrm;
+  __syncthreads();
+  for (int i = tid; i < KDE_EXP_TAB; i += LCV_THREADS) tab[i] = P.exptab[i];  // the heap is no longer needed
+  __syncthreads();
+  LcvDim D;
+  const double hh = __ddiv_rn(__dadd_rn(minm, maxm), 2.0);
+  D.b0 = __dmul_rn(hh, hh);
+  D.ax = __ddiv_rn(__dmul_rn(2.0, minm), __dadd_rn(minm, maxm));
+  D.cx = __ddiv_rn(__dmul_rn(2.0, maxm), __dadd_rn(minm, maxm));
+  lcv_golden_run(D, rec, N, tab, P.ec, P.norm0, P.tol, P.Cg, P.Rg, sh, shf, P.out + dim * 5);
+  if (tid == 0) {
+    P.out[dim * 5 + 3] = minm;
+    P.out[dim * 5 + 4] = maxm;
   }
 }
 
@@ -187,6 +302,53 @@ struct Golden {
 };
 
 }  // namespace
+
+// kde!(points) bandwidths for N <= LCV_FUSED_MAX points resident on the device (point i at d_points + i * d): one launch on
+// `st`, the d x 5 result block stays in d_out5 (xmin, fmin, calls, minm, maxm per dimension) for the caller to fetch
+// together with its other results; lcv_points_finish turns it into the standard deviations.
+int kde_lcv_points_device(int d, int64_t N, const double *d_points, double *d_out5, cudaStream_t st) {
+  if (N < 2 || N > LCV_FUSED_MAX) KDE_FAIL(3, "kde_lcv (device points): needs 2 <= N <= %d", LCV_FUSED_MAX);
+  Context &c = ctx();
+  const Golden G_;
+  // the weights of the working density, exactly as the host route derives them: kde!(points, [1.0]) -> 1/N, marginal()
+  // renormalises by the sequential sum, ksize's kde! renormalises once more
+  double w1 = 1.0 / (double)N;
+  {
+    double ssum = 0.0;
+    for (int64_t i = 0; i < N; ++i) ssum += w1;
+    w1 = w1 / ssum;
+  }
+  double w2;
+  {
+    double ssum = 0.0;
+    for (int64_t i = 0; i < N; ++i) ssum += w1;
+    w2 = w1 / ssum;
+  }
+  LcvPointsParams P;
+  P.pts = d_points;
+  P.out = d_out5;
+  P.exptab = c.d_exptab;
+  P.ec = make_exp_consts();
+  P.N = (int)N;
+  P.d = d;
+  P.w2 = w2;
+  P.norm0 = std::pow(2.0 * M_PI, 0.5);
+  P.tol = 1e-2;
+  P.Cg = G_.Cg;
+  P.Rg = G_.Rg;
+  lcv_golden_points_kernel<<<d, LCV_THREADS, 0, st>>>(P);
+  KDE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+void lcv_points_finish(int d, const double *out5, double *bw_std_out, int *ncalls_out) {
+  for (int k = 0; k < d; ++k) {
+    const double xmin = out5[5 * k], minm = out5[5 * k + 3], maxm = out5[5 * k + 4];
+    const double ks = xmin * (minm + maxm) / 2.0;  // src/CrossValidation.jl:117
+    bw_std_out[k] = std::sqrt(ks * ks);
+    if (ncalls_out) ncalls_out[k] = (int)out5[5 * k + 2];
+  }
+}
 
 // j0, j1 and allreduce: this process owns the leaf rows [j0, j1) of every nLOO_LL evaluation and the callback sums the
 // partial likelihood (and ORs the zero flag) over the processes -- the multi-GPU split of SURVEY.md 8e.  allreduce ==

@@ -109,3 +109,19 @@ def test_sample_rand_resample_statistics_and_seeding():
     assert e.shape == (1, 5) and np.array_equal(ie, [1, 2, 3, 4, 5])
     with pytest.raises(K.KDEError):
         K.resample(p, 10, ksType="discrete")
+
+
+@pytest.mark.parametrize("d,M,N", [(2, 2, 100), (1, 2, 300), (3, 3, 64), (4, 2, 512), (2, 2, 2), (3, 2, 513), (2, 3, 1500)])
+def test_product_in_one_call_equals_the_two_step_route(d, M, N):
+    """kdeb200_product_kde (Gibbs kernel + on-chip sort / ball-tree statistics / golden sections on device-resident
+    samples) against prodAppxMSGibbsS followed by kde!(pGM): same points, bit-identical bandwidths (N <= 512: fused
+    kernel; above: the two-step route inside the call)."""
+    rng = np.random.default_rng(d * 10 + N)
+    trees = [K.kde(mixture(rng, d, N, 0.2 * j) if N > 3 else rng.normal(size=(d, N)), np.full(d, 0.4)) for j in range(M)]
+    pq = K.prod(trees, seed=77)
+    pts, _ = K.prodAppxMSGibbsS(None, trees, None, None, Niter=5, Np=N, seed=77)
+    ref = K.kde(pts)
+    assert np.array_equal(K.getPoints(pq), pts)
+    assert np.array_equal(K.getBW(pq)[:, 0], K.getBW(ref)[:, 0]), (K.getBW(pq)[:, 0], K.getBW(ref)[:, 0])
+    o = OKDE.kde_lcv(pts)
+    assert relerr(K.getBW(pq)[:, 0] ** 2, o.arrays()["bandwidthMin"][:d]) < 1e-10
