@@ -27,6 +27,7 @@ void lcv_points_finish(int d, const double *out5, double *bw_std_out, int *ncall
 int eval_marginals_device(kdeb200_tree_t bd, const double *d_grid, int64_t G, double *d_out, cudaStream_t st, int *launches);
 int sample_device(kdeb200_tree_t bd, int64_t Np, uint64_t seed, const double *d_randU, const double *d_randN,
                   double *d_points, int64_t *d_idx, cudaStream_t st, int *launches);
+bool loo_sym_shardable(const kdeb200_tree_s *bd);
 void set_prune_mode(int m);
 int get_prune_mode();
 int pruned_last_stats(double *kept_fraction, int64_t *redo_rows);
@@ -433,8 +434,10 @@ int kdeb200_loo_entropy(kdeb200_tree_t bd, const double *bw_var, double *H_out) 
   KDE_SERIALISE();
   if (int rc = ensure_init()) return rc;
   if (!bd || !H_out) KDE_FAIL(2, "loo_entropy: NULL argument");
-  // in-process multi-GPU: leaf rows block-partitioned, partial sums added in block order
-  const int G = gpus_for(bd->N, 8192);
+  // in-process multi-GPU: leaf rows block-partitioned, partial sums added in block order -- unless the density is in
+  // the range of the symmetric each-pair-once kernel, which on one device beats row shards on a few (the bandwidth loop
+  // kdeb200_kde_lcv shares the triangle of pairs over the devices instead)
+  const int G = loo_sym_shardable(bd) ? 1 : gpus_for(bd->N, 8192);
   std::vector<double> sums(G, 0.0), ms(G, 0.0);
   std::vector<int> flags(G, 0), nl(G, 0);
   int rc = for_each_gpu(G, [&](int g) {

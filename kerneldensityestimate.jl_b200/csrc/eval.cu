@@ -221,7 +221,8 @@ int eval_pruned_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int lo
                        const double *bw_var, double *d_out, cudaStream_t st, int *launches);
 bool pruning_can_help(const kdeb200_tree_s *bd, const double *bw_var);
 bool loo_sym_applicable(const kdeb200_tree_s *bd);
-int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStream_t st, int *launches);
+int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStream_t st, int *launches, int part,
+                   int nparts, double *d_tot);
 
 // 0: brute force everywhere; 1 (default): the error-bounded tile-pruned kernel (eval_pruned.cu, <= 1e-13 relative)
 // serves the leave-one-out LIKELIHOOD path (nLOO_LL / entropy / kde!(points)); 2: also plain FP64 evaluations --
@@ -294,6 +295,18 @@ int eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, int6
   return 0;
 }
 
+// sum_j W_j log L_j (+ zero flag) of leaf-ordered LOO densities d_L of rows q0..q0+n-1
+int loglik_reduce_device(kdeb200_tree_t bd, const double *d_L, int64_t q0, int64_t n, double *d_sum, int *d_flag,
+                         cudaStream_t st, int *launches) {
+  loglik_reduce_kernel<<<1, 1024, 0, st>>>(d_L, bd->d_leaf, bd->SE, bd->d, q0, n, d_sum, d_flag);
+  KDE_CUDA(cudaGetLastError());
+  if (launches) *launches += 1;
+  return 0;
+}
+
+// may the all-rows LOO sums of this density be shared out over the GPUs of the set by row block (symmetric kernel)?
+bool loo_sym_shardable(const kdeb200_tree_s *bd) { return g_prune_mode >= 1 && loo_sym_applicable(bd); }
+
 int loo_partial_device(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int64_t j1, double *d_sum, int *d_flag,
                        cudaStream_t st, int *launches) {
   const int64_t n = j1 - j0;
@@ -303,7 +316,7 @@ int loo_partial_device(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int6
   // and small / very large densities: the row-by-row kernels
   int rc;
   if (g_prune_mode >= 1 && j0 == 0 && j1 == bd->N && loo_sym_applicable(bd))
-    rc = loo_sym_device(bd, bw_var, d_L, st, launches);
+    rc = loo_sym_device(bd, bw_var, d_L, st, launches, 0, 1, nullptr);
   else
     rc = eval_device(bd, nullptr, n, 1, j0, false, bw_var, d_L, st, launches, g_prune_mode >= 1 ? 1 : 0);
   if (rc) return rc;

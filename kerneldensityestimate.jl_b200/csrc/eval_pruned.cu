@@ -677,6 +677,7 @@ struct SymParams {
   const unsigned int *count;  // kept tiles per row block
   int words;
   int S;                 // CTAs per row block: CTA (b, s) takes the s-th share of the block's kept tiles
+  int part, nparts;      // in-process multi-GPU: this device owns the row blocks b with b % nparts == part
   double *rowpart;       // S x N partial row sums (zeroed before the launch)
   double *colpart;       // nrb x N
 };
@@ -703,6 +704,7 @@ __global__ void __launch_bounds__(EV_THREADS) loo_sym_kernel(const __grid_consta
   const int TN = E.tile_nodes;
   const int ntile = (int)((E.N + TN - 1) / TN);
   const int blk = (int)P.order[blockIdx.x / P.S], share = (int)(blockIdx.x % P.S);
+  if (blk % P.nparts != P.part) return;  // another GPU's row block
   const uint32_t *row = P.mask + (int64_t)blk * P.words;
   // this CTA's share of the block's kept tiles: ordinals [k0, k1)
   const int kept = (int)P.count[blk], per = (kept + P.S - 1) / P.S;
@@ -847,6 +849,36 @@ __global__ void loo_sym_finalize_kernel(const __grid_constant__ SymParams S, int
   out[j] = v;
 }
 
+// multi-GPU: what THIS device contributes to every row j -- its own rows' sums and the column credits of its row blocks
+__global__ void loo_sym_partial_kernel(const __grid_constant__ SymParams S, int bq, double *tot) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const EvalParams &E = S.E;
+  if (j >= E.N) return;
+  const int t = (int)(j / E.tile_nodes);
+  const int bmax = (int)(j / bq);
+  double s = 0.0;
+  for (int y = 0; y < S.S; ++y) s += S.rowpart[(int64_t)y * E.N + j];  // zero unless j is one of this device's rows
+  for (int b = S.part; b <= bmax; b += S.nparts)
+    if ((S.mask[(int64_t)b * S.words + (t >> 5)] >> (t & 31)) & 1u) s += S.colpart[(int64_t)b * E.N + j];
+  tot[j] = s;
+}
+// ... and the primary folds the devices' contributions in device order, then the epilogue / exact-pass list as above
+__global__ void loo_sym_combine_kernel(const __grid_constant__ EvalParams E, const double *tots, int nparts, int SE, int d,
+                                       double thresh, double *out, int64_t *redo, unsigned int *nredo) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= E.N) return;
+  double s = 0.0;
+  for (int g = 0; g < nparts; ++g) s += tots[(int64_t)g * E.N + j];
+  if (!(s >= thresh)) {
+    const unsigned k = atomicAdd(nredo, 1u);
+    redo[k] = j;
+    return;
+  }
+  double v = 0.5 * (s + s) / E.norm;
+  v = v / (1.0 - E.comps[j * SE + d]);
+  out[j] = v;
+}
+
 template <int D, int Q>
 static cudaError_t launch_sym_dq(const SymParams &P, unsigned grid, cudaStream_t st) {
   constexpr int SE = Rec<D>::SE;
@@ -880,8 +912,77 @@ static cudaError_t launch_sym(int d, const SymParams &P, unsigned grid, cudaStre
 
 bool loo_sym_applicable(const kdeb200_tree_s *bd) { return bd->N >= 4096 && bd->N <= SYM_MAX_N; }
 
-// LOO densities of ALL leaves of bd, leaf order, into d_L (N doubles)
-int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStream_t st, int *launches) {
+static int sym_eval_params(kdeb200_tree_t bd, const double *bw_var, EvalParams &E, double *half_ivar) {
+  Context &c = ctx();
+  const int d = bd->d, SE = bd->SE;
+  int TN = 1;
+  while (TN * 2 * SE * 8 <= EV_TILE_BYTES) TN *= 2;
+  E.comps = bd->d_leaf;
+  E.queries = bd->d_leaf;
+  E.N = bd->N;
+  E.M = bd->N;
+  E.q0 = 0;
+  E.qstride = SE;
+  E.perm = nullptr;
+  E.out = nullptr;
+  E.partial = nullptr;
+  E.exptab = c.d_exptab;
+  E.ec = make_exp_consts();
+  E.S = 1;
+  E.chunk = 0;
+  E.tile_nodes = TN;
+  double norm = std::pow(2.0 * M_PI, (double)d / 2.0);
+  for (int k = 0; k < d; ++k) {
+    const double v = bw_var ? bw_var[k] : bd->hvar[k];
+    if (!(v > 0.0) || !std::isfinite(v)) KDE_FAIL(5, "eval: bandwidth variance must be finite and > 0 (dim %d: %g)", k + 1, v);
+    E.ich[k] = -0.5 / v;
+    if (half_ivar) half_ivar[k] = 0.5 / v;
+    norm *= std::sqrt(v);
+  }
+  E.norm = norm;
+  return 0;
+}
+
+// multi-GPU, on the primary: fold the nparts contribution vectors (d_tots: nparts x N) into the LOO densities d_L
+int loo_sym_combine_device(kdeb200_tree_t bd, const double *bw_var, const double *d_tots, int nparts, double *d_L,
+                           cudaStream_t st, int *launches) {
+  Context &c = ctx();
+  const int d = bd->d, SE = bd->SE;
+  const int64_t N = bd->N;
+  EvalParams E;
+  if (int rc = sym_eval_params(bd, bw_var, E, nullptr)) return rc;
+  E.out = d_L;
+  const double thresh = PR_DELTA * bd->wtotal / PR_REL;
+  char *base = nullptr;
+  const size_t b_redo = (sizeof(int64_t) * (size_t)N + 255) & ~(size_t)255;
+  KDE_CUDA(cudaMallocAsync(&base, b_redo + 256, st));
+  int64_t *d_redo = reinterpret_cast<int64_t *>(base);
+  unsigned int *d_nredo = reinterpret_cast<unsigned int *>(base + b_redo);
+  KDE_CUDA(cudaMemsetAsync(d_nredo, 0, 256, st));
+  loo_sym_combine_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(E, d_tots, nparts, SE, d, thresh, d_L, d_redo, d_nredo);
+  KDE_CUDA(cudaGetLastError());
+  PrunedParams R;
+  R.E = E;
+  R.mask = nullptr;
+  R.qidx = nullptr;
+  R.order = nullptr;
+  R.words = 0;
+  R.thresh = thresh;
+  R.redo = d_redo;
+  R.nredo = d_nredo;
+  const unsigned redo_grid = (unsigned)(N < 4 * c.sm_count ? N : 4 * c.sm_count);
+  redo_rows_kernel<<<redo_grid, 256, 0, st>>>(R, d, SE, 1);
+  KDE_CUDA(cudaGetLastError());
+  if (launches) *launches += 2;
+  KDE_CUDA(cudaFreeAsync(base, st));
+  return 0;
+}
+
+// LOO densities of ALL leaves of bd, leaf order, into d_L (N doubles).  nparts > 1 (in-process multi-GPU): only the row
+// blocks b % nparts == part are evaluated here and d_tot (N doubles) receives this device's contribution to every row;
+// the primary adds the contributions up with loo_sym_combine_device.
+int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStream_t st, int *launches, int part,
+                   int nparts, double *d_tot) {
   Context &c = ctx();
   const int d = bd->d, SE = bd->SE;
   const int64_t N = bd->N;
@@ -925,7 +1026,8 @@ int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStr
   // CTAs per row block: the triangle makes the blocks' work differ by two orders of magnitude, and there are few
   // blocks (98 at N = 100k) -- split every block's kept tiles into S shares so that the launch is >= ~8 waves of
   // similar units, longest first
-  int nsplit = (8 * 3 * c.sm_count + nrb - 1) / nrb;
+  const int nown = (nrb + nparts - 1) / nparts;
+  int nsplit = (8 * 3 * c.sm_count + nown - 1) / nown;
   if (nsplit > 32) nsplit = 32;
   if (nsplit < 1) nsplit = 1;
   const size_t b_row = up(sizeof(double) * (size_t)N * nsplit);
@@ -985,12 +1087,21 @@ int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStr
   S.words = words;
   S.count = c_in;
   S.S = nsplit;
+  S.part = part;
+  S.nparts = nparts;
   S.rowpart = d_row;
   S.colpart = d_col;
   cudaError_t e = launch_sym(d, S, (unsigned)nrb * (unsigned)nsplit, st);
   if (e != cudaSuccess) {
     cudaFreeAsync(base, st);
     KDE_FAIL(100 + (int)e, "loo (symmetric) kernel launch: %s", cudaGetErrorString(e));
+  }
+  if (nparts > 1) {
+    loo_sym_partial_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, bq, d_tot);
+    KDE_CUDA(cudaGetLastError());
+    if (launches) *launches += 5;
+    KDE_CUDA(cudaFreeAsync(base, st));
+    return 0;
   }
   loo_sym_finalize_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, bq, SE, d, thresh, d_L, d_redo, d_nredo);
   KDE_CUDA(cudaGetLastError());

@@ -33,6 +33,13 @@ int tree_destroy(kdeb200_tree_t t);
 int tree_on(kdeb200_tree_t t, int slot, kdeb200_tree_t *out);
 int loo_partial_device(kdeb200_tree_t bd, const double *bw_var, int64_t j0, int64_t j1, double *d_sum, int *d_flag,
                        cudaStream_t st, int *launches);
+bool loo_sym_shardable(const kdeb200_tree_s *bd);
+int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStream_t st, int *launches, int part,
+                   int nparts, double *d_tot);
+int loo_sym_combine_device(kdeb200_tree_t bd, const double *bw_var, const double *d_tots, int nparts, double *d_L,
+                           cudaStream_t st, int *launches);
+int loglik_reduce_device(kdeb200_tree_t bd, const double *d_L, int64_t q0, int64_t n, double *d_sum, int *d_flag,
+                         cudaStream_t st, int *launches);
 
 constexpr int LCV_FUSED_MAX = 512;  // one row per thread and a single component tile: the sums of eval.cu at S = 1
 constexpr int LCV_THREADS = 1024;   // == the block of loglik_reduce_kernel (same reduction tree)
@@ -495,7 +502,7 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
     }
     double xmin() const { return (f1 < f2) ? x1 : x2; }
   };
-  const int G = (j1 - j0 >= 8192 * (int64_t)multi_count()) ? multi_count() : 1;
+  int G = (j1 - j0 >= 8192 * (int64_t)multi_count()) ? multi_count() : 1;
   std::vector<kdeb200_tree_t> trees(d, nullptr);
   std::vector<Search> S(d);
   std::vector<double> b(d);
@@ -541,6 +548,35 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
     }
     for (int k = 0; k < d && rc == 0; ++k) rc = tree_on(trees[k], g, &gp[g].t[k]);
   }
+  // In-process multi-GPU with all rows in this process and densities in the symmetric kernel's range: the devices share
+  // the TRIANGLE of pairs instead of the rows.  Device g evaluates the row blocks b = g (mod G) once per unordered pair
+  // and sends its contribution to every row (N doubles) straight into the primary's memory over NVLink (peer copy on its
+  // own stream + an event the primary's stream waits on); the primary folds the G vectors in device order and reduces
+  // the likelihood.  No host round trip between the devices, one synchronisation (of the primary) per step.
+  const bool sym_multi = rc == 0 && G > 1 && !allreduce && j0 == 0 && j1 == N && loo_sym_shardable(trees[0]);
+  std::vector<double *> d_tot(G, nullptr);
+  std::vector<cudaEvent_t> ev(G, nullptr);
+  double *d_all0 = nullptr, *d_L0 = nullptr;
+  if (sym_multi) {
+    for (int g = 0; g < G && rc == 0; ++g) {
+      ScopedDevice sd(g);
+      cudaError_t e = cudaMallocAsync(&d_tot[g], sizeof(double) * (size_t)d * N, ctx().stream);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming);
+      if (e != cudaSuccess) {
+        set_error("kde_lcv: multi-GPU buffers: %s", cudaGetErrorString(e));
+        rc = 100 + (int)e;
+      }
+    }
+    if (rc == 0) {
+      ScopedDevice sd(0);
+      cudaError_t e = cudaMallocAsync(&d_all0, sizeof(double) * (size_t)d * G * N, ctx().stream);
+      if (e == cudaSuccess) e = cudaMallocAsync(&d_L0, sizeof(double) * (size_t)N, ctx().stream);
+      if (e != cudaSuccess) {
+        set_error("kde_lcv: multi-GPU buffers: %s", cudaGetErrorString(e));
+        rc = 100 + (int)e;
+      }
+    }
+  }
   std::vector<int> active;
   std::vector<double> sums(d);
   std::vector<int> flags(d);
@@ -554,6 +590,54 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
       const double alpha = S[k].pending();
       a2[k] = alpha * alpha;  // src/CrossValidation.jl:17
       b[k] = b[k] * a2[k];    // updateBandwidth!(bd, bd.bandwidth * alpha)
+    }
+    if (sym_multi) {
+      for (int g = 0; g < G && rc == 0; ++g) {
+        ScopedDevice sd(g);
+        Context &cg = ctx();
+        for (int k : active) {
+          double *tot = d_tot[g] + (size_t)k * N;
+          rc = loo_sym_device(gp[g].t[k], &b[k], nullptr, cg.stream, &launches, g, G, tot);
+          if (rc) break;
+          cudaError_t e = cudaMemcpyPeerAsync(d_all0 + ((size_t)k * G + g) * N, ctx_at(0).device, tot, cg.device,
+                                              sizeof(double) * (size_t)N, cg.stream);
+          if (e != cudaSuccess) {
+            set_error("kde_lcv: peer copy from GPU slot %d: %s", g, cudaGetErrorString(e));
+            rc = 100 + (int)e;
+            break;
+          }
+        }
+        if (!rc && cudaEventRecord(ev[g], cg.stream) != cudaSuccess) rc = 100;
+      }
+      if (!rc) {
+        ScopedDevice sd(0);
+        Context &c0 = ctx();
+        for (int g = 1; g < G; ++g) cudaStreamWaitEvent(c0.stream, ev[g], 0);
+        for (int k : active) {
+          rc = loo_sym_combine_device(gp[0].t[k], &b[k], d_all0 + (size_t)k * G * N, G, d_L0, c0.stream, &launches);
+          if (!rc)
+            rc = loglik_reduce_device(gp[0].t[k], d_L0, 0, N, gp[0].d_res + 2 * k, reinterpret_cast<int *>(gp[0].d_res + 2 * k + 1),
+                                      c0.stream, &launches);
+          if (rc) break;
+        }
+        if (!rc) {
+          cudaError_t e = cudaMemcpyAsync(gp[0].h_res.data(), gp[0].d_res, sizeof(double) * 2 * d, cudaMemcpyDeviceToHost, c0.stream);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(c0.stream);
+          if (e != cudaSuccess) {
+            set_error("kde_lcv: LOO kernels (multi-GPU, symmetric): %s", cudaGetErrorString(e));
+            rc = 100 + (int)e;
+          }
+        }
+      }
+      if (rc) break;
+      for (int k : active) {
+        int f;
+        std::memcpy(&f, &gp[0].h_res[2 * k + 1], sizeof(int));
+        const double H = f ? std::numeric_limits<double>::infinity() : -gp[0].h_res[2 * k];
+        b[k] = b[k] / a2[k];
+        S[k].feed(H);
+      }
+      continue;
     }
     for (int g = 0; g < G && rc == 0; ++g) {  // queue everything, no host wait in between
       ScopedDevice sd(g);
@@ -609,7 +693,15 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
   }
   for (int g = 0; g < G; ++g) {
     ScopedDevice sd(g);
+    if (sym_multi) cudaStreamSynchronize(ctx().stream);  // peers may still be copying into the primary's buffers
     if (gp[g].d_res) cudaFreeAsync(gp[g].d_res, ctx().stream);
+    if (d_tot[g]) cudaFreeAsync(d_tot[g], ctx().stream);
+    if (ev[g]) cudaEventDestroy(ev[g]);
+  }
+  {
+    ScopedDevice sd(0);
+    if (d_all0) cudaFreeAsync(d_all0, ctx().stream);
+    if (d_L0) cudaFreeAsync(d_L0, ctx().stream);
   }
   for (int k = 0; k < d; ++k)
     if (trees[k]) tree_destroy(trees[k]);
