@@ -268,22 +268,46 @@ def secondary_single(K, dfma, mufu, args):
     N = args.c3_n
     pts = mixture(np.random.default_rng(3), 4, N)
     p1 = K.marginal(K.kde(pts, [1.0]), [1])
-    K.entropy(p1)
-    t0 = time.perf_counter(); H = K.entropy(p1); one = time.perf_counter() - t0
-    ms, nl = K.last_kernel_ms()
     evals = float(N) * N
+
+    def one_nloo(mode):
+        K.set_pruning(mode)
+        K.entropy(p1)
+        t0 = time.perf_counter(); H = K.entropy(p1); wall = time.perf_counter() - t0
+        ms, nl = K.last_kernel_ms()
+        return H, wall, ms, nl
+    H0, one0, ms0, nl0 = one_nloo(0)   # reference-order brute force: every ordered pair (eval_kernel<1,6,true>)
+    H, one, ms, nl = one_nloo(1)       # default: each unordered pair once + tile pruning (loo_sym_kernel<1,8>)
+    kept, redo = K.pruned_stats()
+    rsym = issued_record("loo_sym_c3")
+    sym_roof = {"bound": "fp64_fma_pipe", "kernel": "loo_sym_kernel<1,8>", "kernel_ms": ms,
+                # per UNORDERED pair: 2d+1 (distance) + 14 (exp) + 2 (credit both rows) = 19 slots at d = 1
+                "algorithmic_fp64_slots_per_unordered_pair": 19, "unordered_pairs_evaluated": evals * kept,
+                "frac": evals * kept * 19 / (ms * 1e-3) / dfma, "peak": dfma * 2 / 1e12, "unit": "TFLOP/s",
+                "achieved": evals * kept * 19 * 2 / (ms * 1e-3) / 1e12,
+                "note": "kept = fraction of (row block x tile) pairs evaluated: ~0.5 is the triangle, less is pruning; kernel_ms "
+                        "includes the box / mask / order / finalize / exact-pass launches",
+                "issued_fp64_instr_per_nominal_eval": None, "issued_frac": None}
+    if rsym:
+        sym_roof["issued_fp64_instr_per_nominal_eval"] = rsym["fp64_lane_instr_per_unit"]
+        sym_roof["issued_source"] = "profiles/ncu_issued.json[loo_sym_c3] (source hash %s)" % rsym["source_hash"]
     K.kde(pts[:, :3000])
     t0 = time.perf_counter(); pk = K.kde(pts); total = time.perf_counter() - t0
     K.set_pruning(0)
     t0 = time.perf_counter(); pk0 = K.kde(pts); total_brute = time.perf_counter() - t0
     K.set_pruning(1)
     rec = {"workload": "C3: kde!(points) LOOCV bandwidth selection, %d points, 4-D" % N,
-           "one_nLOO_LL": {"value": evals / (ms * 1e-3), "unit": "evals/s", "kernel_ms": ms, "wall_ms": one * 1e3, "launches": nl,
-                           "H": H, "roofline": eval_roofline("eval_c3", 1, evals, ms, dfma, "eval_kernel<1,6,true>")},
+           "one_nLOO_LL": {"value": evals / (ms * 1e-3), "unit": "evals/s (nominal N x N)", "kernel_ms": ms, "wall_ms": one * 1e3,
+                           "launches": nl, "H": H, "kept_pair_fraction": kept, "rows_recomputed_exactly": redo,
+                           "rel_diff_vs_reference_order_sum": abs(H - H0) / abs(H0), "roofline": sym_roof,
+                           "speedup_vs_brute_force": ms0 / ms},
+           "one_nLOO_LL_brute_force": {"value": evals / (ms0 * 1e-3), "unit": "evals/s", "kernel_ms": ms0, "wall_ms": one0 * 1e3,
+                                       "launches": nl0, "H": H0,
+                                       "roofline": eval_roofline("eval_c3", 1, evals, ms0, dfma, "eval_kernel<1,6,true>")},
            "full_kde": {"value": total, "unit": "s", "higher_is_better": False, "bandwidth": K.getBW(pk)[:, 0].tolist(),
                         "brute_force_only_s": total_brute, "bandwidth_brute_force_only": K.getBW(pk0)[:, 0].tolist(),
-                        "note": "default policy: the LOO likelihood uses the error-bounded pruned kernel (<= 1e-13 relative) "
-                                "wherever the bandwidth is small enough to drop tiles, the brute-force kernel otherwise",
+                        "note": "default policy: the LOO likelihood is summed each-pair-once (symmetric kernel) and tile-pruned, "
+                                "within 1e-13 relative of the reference-order sum; kdeb200_set_pruning(0) = brute force only",
                         "api": "kde_b200.kde(points) -> kdeb200_kde_lcv (host points in, d bandwidths out)",
                         "h2d_bytes": 8 * 2 * N * 4, "d2h_bytes": 8 * 4}}
     o1 = O.OKDE.kde_bw(K.getPoints(p1), K.getBW(p1)[:, 0], K.getWeights(p1))
@@ -344,7 +368,28 @@ def secondary_sharded(K, kd, torch, dist, rank, world, dev, args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out["c3"] = {"workload": "C3: kde!(points) LOOCV, %d points, 4-D, rows of every nLOO_LL step sharded over %d GPUs" % (n3, world),
                  "full_kde": {"value": float(t.item()), "unit": "s", "higher_is_better": False, "bandwidth": K.getBW(pk)[:, 0].tolist()},
-                 "scaling": "strong"}
+                 "scaling": "strong", "route": "one process per GPU (torch.distributed): row shards + one vector all-reduce per step"}
+    # The library's own multi-GPU route (kdeb200_init_multi: ONE process drives all GPUs through the C-ABI; the symmetric
+    # LOO kernel shares the triangle of pairs, contributions travel by peer copies).  Rank 0 runs it while the other ranks
+    # wait at the barrier; their contexts stay resident on their GPUs, so this is if anything pessimistic.
+    dist.barrier(); torch.cuda.synchronize()
+    if rank == 0:
+        try:
+            g = K.init_multi(world)
+            rng = np.random.default_rng(SEED)
+            cp5, pos5 = mixture(rng, 3, n), mixture(rng, 3, n)
+            p5 = K.kde(cp5, silverman(cp5))
+            K.evaluateDualTree(p5, pos5[:, :8192 * g])
+            t0 = time.perf_counter(); K.evaluateDualTree(p5, pos5); w5 = time.perf_counter() - t0
+            K.lcv_bandwidths(pts[:, :20000])
+            t0 = time.perf_counter(); bw = K.lcv_bandwidths(pts); w3 = time.perf_counter() - t0
+            out["in_process"] = {"n_gpus": g, "route": "kdeb200_init_multi: one host process, host buffers in and out",
+                                 "c5": {"value": float(n) * n / w5, "unit": "evals/s", "wall_s": w5},
+                                 "c3_lcv_bandwidths": {"value": w3, "unit": "s", "higher_is_better": False, "bandwidth": bw.tolist()}}
+            p5._invalidate()
+        finally:
+            K.init_multi(1)
+    dist.barrier()
     return out
 
 

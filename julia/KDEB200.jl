@@ -24,6 +24,19 @@ end
 
 init(device::Integer=0) = check(ccall((:kdeb200_init, LIB), Cint, (Cint,), device))
 
+# One Julia process drives `ngpus` GPUs (0 = all visible): afterwards gibbs1!, evaluate!, entropy and lcv_bandwidths
+# shard their samples / query points / leaf rows over the set inside the library -- no MPI, no second process.
+init_multi(ngpus::Integer=0) = check(ccall((:kdeb200_init_multi, LIB), Cint, (Cint,), ngpus))
+function multi_count()
+  n = Ref{Cint}(0)
+  check(ccall((:kdeb200_multi_count, LIB), Cint, (Ref{Cint},), n))
+  Int(n[])
+end
+
+# setForceEvalDirect!(flag) of the reference (src/DualTree01.jl:3-9): false selects the error-bounded pruned kernel
+# (every value within 1e-13 of the brute-force sum; the reference's dual tree: errTol = 1e-3) for evaluate!
+setForceEvalDirect!(flag::Bool) = check(ccall((:kdeb200_set_pruning, LIB), Cint, (Cint,), flag ? 1 : 2))
+
 # ---- S0: device-resident BallTreeDensity -------------------------------------------------
 mutable struct DeviceTree
   h::Ptr{Cvoid}
@@ -161,6 +174,40 @@ function lcv_bandwidths_sharded(points::Matrix{Float64}, j0::Integer, j1::Intege
     (Cint, Int64, Ptr{Float64}, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cint}),
     d, N, points, j0, j1, allreduce, C_NULL, bw, C_NULL))
   return bw
+end
+
+# `*` (src/MSGibbs01.jl:707-726) in one call: product samples + the LOOCV bandwidths of kde!(pGM); up to 512 samples never
+# leave the device between the Gibbs kernel and the refit.  Returns the product density.
+function product(trees::Vector{BallTreeDensity}; addEntropy::Bool=true, Niter::Int=5, seed::UInt64=rand(UInt64))
+  Np = round(Int, sum(Npts.(trees)) / length(trees))
+  d = Ndim(trees[1])
+  dts = [DeviceTree(t) for t in trees]
+  hs = Ptr{Cvoid}[t.h for t in dts]
+  pts = zeros(d, Np); bw = zeros(d)
+  GC.@preserve dts hs pts bw check(ccall((:kdeb200_product_kde, LIB), Cint,
+    (Ptr{Ptr{Cvoid}}, Cint, Int64, Cint, Cint, Ptr{UInt8}, UInt64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Cint}),
+    hs, length(trees), Np, Niter, addEntropy, C_NULL, seed, pts, C_NULL, bw, C_NULL))
+  return kde!(pts, bw)
+end
+
+# sample(npd, Npts) (src/KDE01.jl:164-183) on the device; Philox(seed) variates (Julia's RNG streams can be injected as
+# randU (Npts) / randN (d x Npts) through the C entry point directly)
+function sample(npd::BallTreeDensity, Np::Int; seed::UInt64=rand(UInt64))
+  dt = DeviceTree(npd; gibbs=false)
+  pts = zeros(Ndim(npd), Np); ind = zeros(Int, Np)
+  GC.@preserve dt pts ind check(ccall((:kdeb200_sample, LIB), Cint,
+    (Ptr{Cvoid}, Int64, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}), dt.h, Np, seed, C_NULL, C_NULL, pts, ind))
+  return pts, ind
+end
+
+# every 1-D marginal on its own grid in one launch (getKDEMax, src/DualTree01.jl:558-569): grids is G x d (column k = the
+# abscissae of dimension k, i.e. the C side's d x G row-major), result likewise
+function eval_marginals(p::BallTreeDensity, grids::Matrix{Float64})
+  dt = DeviceTree(p; gibbs=false)
+  out = similar(grids)
+  GC.@preserve dt grids out check(ccall((:kdeb200_eval_marginals, LIB), Cint,
+    (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}), dt.h, grids, size(grids, 1), out))
+  return out
 end
 
 # nLOO_LL with the device tree reused across the ~20 golden-section steps of one ksize call

@@ -1,18 +1,22 @@
-set -x
-cd $GRAFT_REPO_ROOT
+#!/bin/bash
+# compute-sanitizer over the round-2 kernels: tools/sanitizer_run.sh   (writes gpurun_out/r02_sanitizer.txt)
+cd "$(dirname "$0")/.."
 S=/usr/local/cuda/bin/compute-sanitizer
-out=gpurun_out/sanitizer.txt
-echo "compute-sanitizer on the B200 box (round 1, final kernels)" > $out
+out=gpurun_out/r02_sanitizer.txt
+mkdir -p gpurun_out
+echo "compute-sanitizer on the B200 box (round 2 kernels)" > $out
+run() {  # label, tool, pytest selection...
+  echo "== $1" >> $out
+  local tool=$2; shift 2
+  timeout 600 $S --tool $tool python -m pytest "$@" -m gpu -q -x 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|hazard" | tail -4 >> $out
+}
 echo "== memcheck: smoke()" >> $out
 timeout 300 $S --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -v "^$" | tail -3 >> $out
-echo "== racecheck: smoke()" >> $out
-timeout 300 $S --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 >> $out
-echo "== memcheck: native LCV (fused + host loop), eval-only handles" >> $out
-timeout 400 $S --tool memcheck python -m pytest tests/test_gpu_eval.py -m gpu -q -x -k "native_lcv or eval_only or loo_eval" 2>&1 | tail -4 >> $out
-echo "== racecheck: fused golden-section kernel" >> $out
-timeout 400 $S --tool racecheck python -m pytest tests/test_gpu_eval.py -m gpu -q -x -k "native_lcv_equals_stepwise_mirror and (100 or 257)" 2>&1 | tail -4 >> $out
-echo "== memcheck: Gibbs dynamic scheduling, tiny schedules" >> $out
-timeout 400 $S --tool memcheck python -m pytest tests/test_gpu_gibbs.py -m gpu -q -x -k "many_batches or mixed_sizes" 2>&1 | tail -4 >> $out
-echo "== racecheck: Gibbs dynamic scheduling" >> $out
-timeout 400 $S --tool racecheck python -m pytest tests/test_gpu_gibbs.py -m gpu -q -x -k "many_batches and 129" 2>&1 | tail -4 >> $out
+run "memcheck: pruned evaluation + symmetric LOO (boxes, mask, order, exact pass)" memcheck tests/test_gpu_pruned.py -k "far_queries or symmetric and (5000 or 9000) or bounded_eval_matches and 9999"
+run "racecheck: symmetric LOO kernel (shared-memory column credits)" racecheck tests/test_gpu_pruned.py -k "symmetric and 5000"
+run "memcheck: warp-per-chain + thread-per-chain Gibbs, tiny schedules, masks, label recording" memcheck tests/test_gpu_gibbs.py -k "many_batches or partial_dim_mask or label_recording or mixed_sizes"
+run "racecheck: warp-per-chain Gibbs" racecheck tests/test_gpu_gibbs.py -k "warp and many_batches and 129"
+run "memcheck: fused product (on-chip sort + ball-tree statistics + golden sections), sample, marginals" memcheck tests/test_gpu_extras.py -k "product_in_one_call and (100 or 300 or 512) or sample_with_injected or eval_marginals and 777"
+run "racecheck: fused product kernel" racecheck tests/test_gpu_extras.py -k "product_in_one_call and 3-3-64"
+run "memcheck: in-process multi-GPU (contexts on one device), schedule cache" memcheck tests/test_gpu_multi.py -k "gibbs_sharded and oversubscribed or small_calls"
 cat $out
