@@ -135,6 +135,16 @@ static int init_multi_devices(const int *devices, int n) {
       if (can) {
         cudaSetDevice(g_ctx[a].device);
         if (cudaDeviceEnablePeerAccess(g_ctx[b].device, 0) != cudaSuccess) cudaGetLastError();  // already enabled
+        // stream-ordered allocations come from the device's memory pool, which has its own access list: without this
+        // every peer copy of pool memory (tree replicas, the LOO contribution vectors) is staged through the host
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, g_ctx[a].device) == cudaSuccess) {
+          cudaMemAccessDesc desc = {};
+          desc.location.type = cudaMemLocationTypeDevice;
+          desc.location.id = g_ctx[b].device;
+          desc.flags = cudaMemAccessFlagsProtReadWrite;
+          if (cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) cudaGetLastError();
+        }
       }
     }
   KDE_CUDA(cudaSetDevice(g_ctx[0].device));

@@ -12,7 +12,9 @@
 //                        dimension i on chip (points in shared memory, one thread per row, the same
 //                        sequential leaf-order sums and the same 1024-slot reduction tree as eval.cu)
 //   larger N           : host golden loop over the tiled LOO kernel of eval.cu, one scalar back per step
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <thread>
@@ -363,6 +365,7 @@ void lcv_points_finish(int d, const double *out5, double *bw_std_out, int *ncall
 int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb200_allreduce_v_fn allreduce,
             void *user, double *bw_std_out, int *ncalls_out) {
   if (int rc = ensure_init()) return rc;
+  const double t_enter = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   if (d < 1) KDE_FAIL(3, "kde_lcv: d must be >= 1");
   if (N < 2) KDE_FAIL(3, "kde_lcv: at least two points are needed for cross validation");
   if (2 * N >= (int64_t)std::numeric_limits<int32_t>::max()) KDE_FAIL(3, "kde_lcv: N too large");
@@ -580,7 +583,14 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
   std::vector<int> active;
   std::vector<double> sums(d);
   std::vector<int> flags(d);
+  const bool trace = getenv("KDEB200_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_loop = now();
+  double t_queue = 0.0;
+  int nsteps = 0;
   while (rc == 0) {
+    const double t_s0 = now();
+    ++nsteps;
     active.clear();
     for (int k = 0; k < d; ++k)
       if (!S[k].done) active.push_back(k);
@@ -609,6 +619,7 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
         }
         if (!rc && cudaEventRecord(ev[g], cg.stream) != cudaSuccess) rc = 100;
       }
+      t_queue += now() - t_s0;
       if (!rc) {
         ScopedDevice sd(0);
         Context &c0 = ctx();
@@ -691,6 +702,9 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
       S[k].feed(H);
     }
   }
+  if (trace)
+    fprintf(stderr, "[kdeb200] kde_lcv N=%lld d=%d G=%d sym_multi=%d: setup %.1f ms, %d lock-step rounds in %.1f ms (host queueing %.1f ms)\n",
+            (long long)N, d, G, (int)sym_multi, t_loop - t_enter, nsteps, now() - t_loop, t_queue);
   for (int g = 0; g < G; ++g) {
     ScopedDevice sd(g);
     if (sym_multi) cudaStreamSynchronize(ctx().stream);  // peers may still be copying into the primary's buffers

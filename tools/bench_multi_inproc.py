@@ -19,8 +19,11 @@ for label, G in (("one_gpu", 1), ("all_gpus", 0)):
     K.evaluateDualTree(p, pos[:, :8192 * g])       # replicate the tree, warm every device
     t0 = time.perf_counter(); v = K.evaluateDualTree(p, pos); t5 = time.perf_counter() - t0
     ms5, _ = K.last_kernel_ms()
-    K.lcv_bandwidths(x3[:, :20000])
-    t0 = time.perf_counter(); bw = K.lcv_bandwidths(x3); t3 = time.perf_counter() - t0
+    K.lcv_bandwidths(x3)                           # warm every device (lazy kernel loading, tree replicas, pools)
+    ts = []
+    for rep in range(3):
+        t0 = time.perf_counter(); bw = K.lcv_bandwidths(x3); ts.append(time.perf_counter() - t0)
+    t3 = min(ts)
     out[label] = {"n_gpus": g, "c5_wall_s": t5, "c5_slowest_kernel_ms": ms5, "c5_evals_per_s": float(n5) * n5 / t5,
                   "c3_kde_wall_s": t3, "c3_bandwidth": bw.tolist(), "c5_checksum": float(v.sum())}
 out["c5_speedup"] = out["one_gpu"]["c5_wall_s"] / out["all_gpus"]["c5_wall_s"]
