@@ -373,27 +373,11 @@ def secondary_sharded(K, kd, torch, dist, rank, world, dev, args):
     out["c3"] = {"workload": "C3: kde!(points) LOOCV, %d points, 4-D, rows of every nLOO_LL step sharded over %d GPUs" % (n3, world),
                  "full_kde": {"value": float(t.item()), "unit": "s", "higher_is_better": False, "bandwidth": K.getBW(pk)[:, 0].tolist()},
                  "scaling": "strong", "route": "one process per GPU (torch.distributed): row shards + one vector all-reduce per step"}
-    # The library's own multi-GPU route (kdeb200_init_multi: ONE process drives all GPUs through the C-ABI; the symmetric
-    # LOO kernel shares the triangle of pairs, contributions travel by peer copies).  Rank 0 runs it while the other ranks
-    # wait at the barrier; their contexts stay resident on their GPUs, so this is if anything pessimistic.
-    dist.barrier(); torch.cuda.synchronize()
-    if rank == 0:
-        try:
-            g = K.init_multi(world)
-            rng = np.random.default_rng(SEED)
-            cp5, pos5 = mixture(rng, 3, n), mixture(rng, 3, n)
-            p5 = K.kde(cp5, silverman(cp5))
-            K.evaluateDualTree(p5, pos5[:, :8192 * g])
-            t0 = time.perf_counter(); K.evaluateDualTree(p5, pos5); w5 = time.perf_counter() - t0
-            K.lcv_bandwidths(pts)  # warm every device (lazy kernel loading, tree replicas, pools)
-            t0 = time.perf_counter(); bw = K.lcv_bandwidths(pts); w3 = time.perf_counter() - t0
-            out["in_process"] = {"n_gpus": g, "route": "kdeb200_init_multi: one host process, host buffers in and out",
-                                 "c5": {"value": float(n) * n / w5, "unit": "evals/s", "wall_s": w5},
-                                 "c3_lcv_bandwidths": {"value": w3, "unit": "s", "higher_is_better": False, "bandwidth": bw.tolist()}}
-            p5._invalidate()
-        finally:
-            K.init_multi(1)
-    dist.barrier()
+    # The library's own multi-GPU route (kdeb200_init_multi: ONE process drives all GPUs through the C-ABI, symmetric LOO
+    # kernel sharing the triangle of pairs, peer copies) cannot be timed from inside a torchrun job -- the other ranks'
+    # NCCL barrier kernels would occupy the GPUs it drives -- so it is measured by tools/bench_multi_inproc.py and
+    # examples/product_multi_c.c (profiles/r02_inproc_n{2,4,8}.json, r02_product_multi_c_n{2,4,8}.json).
+    out["in_process_route"] = "see profiles/r02_inproc_n%d.json and profiles/r02_product_multi_c_n%d.json" % (world, world)
     return out
 
 

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -602,22 +603,44 @@ int kde_lcv(int d, int64_t N, const double *points, int64_t j0, int64_t j1, kdeb
       b[k] = b[k] * a2[k];    // updateBandwidth!(bd, bd.bandwidth * alpha)
     }
     if (sym_multi) {
-      for (int g = 0; g < G && rc == 0; ++g) {
+      // one host thread per device queues that device's launches (a dozen per dimension: boxes, mask, order, kernel,
+      // partial sums, peer copy); queued from a single thread they cost as much as the kernels at 8 GPUs
+      std::vector<int> rcs(G, 0), nl(G, 0);
+      std::vector<std::string> errs(G);
+      auto queue_device = [&](int g) {
         ScopedDevice sd(g);
         Context &cg = ctx();
         for (int k : active) {
           double *tot = d_tot[g] + (size_t)k * N;
-          rc = loo_sym_device(gp[g].t[k], &b[k], nullptr, cg.stream, &launches, g, G, tot);
-          if (rc) break;
-          cudaError_t e = cudaMemcpyPeerAsync(d_all0 + ((size_t)k * G + g) * N, ctx_at(0).device, tot, cg.device,
-                                              sizeof(double) * (size_t)N, cg.stream);
-          if (e != cudaSuccess) {
-            set_error("kde_lcv: peer copy from GPU slot %d: %s", g, cudaGetErrorString(e));
-            rc = 100 + (int)e;
-            break;
+          int r = loo_sym_device(gp[g].t[k], &b[k], nullptr, cg.stream, &nl[g], g, G, tot);
+          if (!r) {
+            cudaError_t e = cudaMemcpyPeerAsync(d_all0 + ((size_t)k * G + g) * N, ctx_at(0).device, tot, cg.device,
+                                                sizeof(double) * (size_t)N, cg.stream);
+            if (e != cudaSuccess) {
+              set_error("kde_lcv: peer copy from GPU slot %d: %s", g, cudaGetErrorString(e));
+              r = 100 + (int)e;
+            }
+          }
+          if (r) {
+            rcs[g] = r;
+            errs[g] = get_error();
+            return;
           }
         }
-        if (!rc && cudaEventRecord(ev[g], cg.stream) != cudaSuccess) rc = 100;
+        if (cudaEventRecord(ev[g], cg.stream) != cudaSuccess) rcs[g] = 100;
+      };
+      {
+        std::vector<std::thread> th;
+        for (int g = 1; g < G; ++g) th.emplace_back(queue_device, g);
+        queue_device(0);
+        for (auto &t : th) t.join();
+      }
+      for (int g = 0; g < G; ++g) {
+        launches += nl[g];
+        if (rcs[g] && !rc) {
+          set_error("GPU slot %d: %s", g, errs[g].c_str());
+          rc = rcs[g];
+        }
       }
       t_queue += now() - t_s0;
       if (!rc) {
