@@ -518,6 +518,7 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
   if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return fail(e, "sync");  // host vectors die here
   t->device_bytes = total;
   t->slot = c.slot;
+  t->device = c.device;
   t->h_perm = std::move(pr);
   *out = t;
   return 0;
@@ -533,10 +534,11 @@ int tree_on(kdeb200_tree_t t, int slot, kdeb200_tree_t *out) {
   }
   if (t->slot != 0) KDE_FAIL(3, "tree_on: only trees created on the primary device can be replicated");
   if (slot < 0 || slot >= multi_count()) KDE_FAIL(3, "tree_on: slot %d outside the multi-GPU set", slot);
-  if (t->replica[slot]) {
+  if (t->replica[slot] && t->replica[slot]->device == ctx_at(slot).device) {
     *out = t->replica[slot];
     return 0;
   }
+  // (a replica made for another device list -- kdeb200_init_multi_devices was called again -- is left to its pool)
   Context &src = ctx_at(0);
   Context &dst = ctx_at(slot);
   ScopedDevice sd(slot);
@@ -560,6 +562,7 @@ int tree_on(kdeb200_tree_t t, int slot, kdeb200_tree_t *out) {
   rebase(r->d_levperm);
   rebase(r->d_leaf);
   rebase(r->d_perm);
+  r->device = dst.device;
   r->d_leaf32 = nullptr;
   r->d_tilebox = nullptr;
   r->d_cw = nullptr;
@@ -589,7 +592,7 @@ int tree_destroy(kdeb200_tree_t t) {
   if (t->d_cw) cudaFreeAsync(t->d_cw, c.stream);
   for (int s = 1; s < KDEB200_MAX_GPUS; ++s)
     if (kdeb200_tree_s *r = t->replica[s]) {
-      if (s < multi_count() && ctx_at(s).ready) {  // the context may be gone after a re-init: its memory went with it
+      if (s < multi_count() && ctx_at(s).ready && ctx_at(s).device == r->device) {  // else: the set was re-made without this device
         ScopedDevice sd(s);
         cudaDeviceSynchronize();
         if (r->d_base) cudaFreeAsync(r->d_base, ctx_at(s).stream);

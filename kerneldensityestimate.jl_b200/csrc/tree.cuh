@@ -46,6 +46,7 @@ struct kdeb200_tree_s {
   int64_t *d_leaf_of = nullptr; // ... and original index -> leaf position (same allocation as d_cw)
   size_t device_bytes = 0;
   int slot = 0;                 // context slot that owns the device memory (0 = primary)
+  int device = 0;               // ... and its CUDA device
   std::vector<int64_t> h_perm;  // host copy of d_perm (scatter of sharded LOO rows)
   kdeb200_tree_s *replica[KDEB200_MAX_GPUS] = {nullptr};  // copies on the other GPUs of the in-process set (lazy)
 };
