@@ -16,12 +16,13 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 
 # the sources that determine each hot kernel's instruction stream (tools/ncu_issued.py keys its ncu counters by this
 # hash; bench.py refuses to quote issued-instruction numbers measured on other sources)
+# (device code and the host code that shapes a launch; tree.cuh -- the host-side handle struct -- is deliberately not in)
 KERNEL_SOURCES = {
-    "gibbs": ["gibbs_kernel.cuh", "gibbs.cu", "common.cuh", "tree.cuh"],
-    "eval": ["eval.cu", "eval_shared.cuh", "common.cuh", "tree.cuh"],
-    "eval_pruned": ["eval_pruned.cu", "eval_shared.cuh", "common.cuh", "tree.cuh"],
-    "eval_f32": ["eval_f32.cu", "common.cuh", "tree.cuh"],
-    "lcv": ["lcv.cu", "eval_shared.cuh", "common.cuh", "tree.cuh"],
+    "gibbs": ["gibbs_kernel.cuh", "gibbs.cu", "common.cuh"],
+    "eval": ["eval.cu", "eval_shared.cuh", "common.cuh"],
+    "eval_pruned": ["eval_pruned.cu", "eval_shared.cuh", "common.cuh"],
+    "eval_f32": ["eval_f32.cu", "common.cuh"],
+    "lcv": ["lcv.cu", "eval_shared.cuh", "common.cuh"],
 }
 
 
