@@ -255,6 +255,17 @@ def secondary_single(K, dfma, mufu, args):
                      "the Morton sort, box and mask passes in kernel_ms",
                      "frac": evals * kept * ALG_SLOTS_EVAL[3] / (ms * 1e-3) / dfma},
         "speedup_vs_brute_force": rec["f64"]["kernel_ms"] / ms}
+    K.evaluateDualTree(p, pos[:, :8192], precision=K.F32_BOUNDED)
+    t0 = time.perf_counter(); vf = K.evaluateDualTree(p, pos, precision=K.F32_BOUNDED); wall = time.perf_counter() - t0
+    ms, nl = K.last_kernel_ms()
+    kept32, redo32 = K.pruned_stats()
+    rec["f32_bounded"] = {"value": evals / (ms * 1e-3), "unit": "evals/s (nominal N x M)", "kernel_ms": ms, "launches": nl,
+                          "kept_pair_fraction": kept32, "rows_recomputed_in_fp64": redo32,
+                          "max_rel_err_vs_f64": float(np.max(np.abs(vf - ref) / ref)),
+                          "e2e": {"value": evals / wall, "unit": "evals/s (nominal)", "wall_s": wall},
+                          "roofline": {"bound": "mufu_ex2", "frac": evals * kept32 / (ms * 1e-3) / mufu,
+                                       "note": "on the evaluated pairs; kernel_ms includes sort / box / mask passes"},
+                          "speedup_vs_fp32_brute_force": rec["f32"]["kernel_ms"] / ms}
     o = O.OKDE.kde_bw(pts, bw)
     mq = 128 * cores
     t0 = time.perf_counter(); ov = o.evaluate(pos[:, :mq], nthreads=cores); tn = time.perf_counter() - t0

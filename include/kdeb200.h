@@ -38,6 +38,8 @@ extern "C" {
 #define KDEB200_F32 1 /* FP32 arithmetic with MUFU ex2 (evaluation only, 1e-5; far-tail values flush to 0) */
 #define KDEB200_F64_BOUNDED 2 /* FP64, tile-pruned with a guaranteed bound: every value within 1e-13 relative of the
                                  brute-force sum (the counterpart of the reference's dual-tree evaluation) */
+#define KDEB200_F32_BOUNDED 3 /* FP32 arithmetic through the same pruning (window 8.6 bandwidths, rows below the bound
+                                 recomputed in FP64): 1e-5 like KDEB200_F32; leave-one-out calls run unpruned */
 
 typedef struct kdeb200_tree_s *kdeb200_tree_t; /* opaque device-resident BallTreeDensity */
 

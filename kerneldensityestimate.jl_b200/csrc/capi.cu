@@ -28,6 +28,7 @@ int eval_marginals_device(kdeb200_tree_t bd, const double *d_grid, int64_t G, do
 int sample_device(kdeb200_tree_t bd, int64_t Np, uint64_t seed, const double *d_randU, const double *d_randN,
                   double *d_points, int64_t *d_idx, cudaStream_t st, int *launches);
 bool loo_sym_shardable(const kdeb200_tree_s *bd);
+int eval_pruned_f32_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, double *d_out, cudaStream_t st, int *launches);
 void set_prune_mode(int m);
 int get_prune_mode();
 int pruned_last_stats(double *kept_fraction, int64_t *redo_rows);
@@ -198,10 +199,14 @@ static int eval_host_block(kdeb200_tree_t bd, const double *pos, int64_t a, int6
   KDE_CUDA(dO.alloc(sizeof(double) * n));
   Timer tm(c);
   int launches = 0;
-  int rc = (precision != KDEB200_F32)
-               ? eval_device(loc, dQ.as<double>(), n, loo, a, scatter, nullptr, dO.as<double>(), c.stream, &launches,
-                             prune_for(precision))
-               : eval_device_f32(loc, dQ.as<double>(), n, loo, dO.as<double>(), c.stream, &launches);
+  int rc;
+  if (precision == KDEB200_F32_BOUNDED && !loo)
+    rc = eval_pruned_f32_device(loc, dQ.as<double>(), n, dO.as<double>(), c.stream, &launches);
+  else if (precision == KDEB200_F32 || precision == KDEB200_F32_BOUNDED)
+    rc = eval_device_f32(loc, dQ.as<double>(), n, loo, dO.as<double>(), c.stream, &launches);
+  else
+    rc = eval_device(loc, dQ.as<double>(), n, loo, a, scatter, nullptr, dO.as<double>(), c.stream, &launches,
+                     prune_for(precision));
   if (rc) return rc;
   tm.stop();
   c.last_launches = launches;
@@ -378,7 +383,9 @@ int kdeb200_eval_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int l
   int rc;
   if (precision == KDEB200_F64 || precision == KDEB200_F64_BOUNDED)
     rc = eval_device(bd, d_pos, M, loo, 0, true, nullptr, d_out, (cudaStream_t)stream, &launches, prune_for(precision));
-  else if (precision == KDEB200_F32)
+  else if (precision == KDEB200_F32_BOUNDED && !loo)
+    rc = eval_pruned_f32_device(bd, d_pos, M, d_out, (cudaStream_t)stream, &launches);
+  else if (precision == KDEB200_F32 || precision == KDEB200_F32_BOUNDED)
     rc = eval_device_f32(bd, d_pos, M, loo, d_out, (cudaStream_t)stream, &launches);
   else
     KDE_FAIL(3, "eval: unknown precision %d", precision);
@@ -391,13 +398,12 @@ int kdeb200_eval(kdeb200_tree_t bd, const double *pos, int64_t M, int loo, int p
   if (int rc = ensure_init()) return rc;
   if (!bd || !p_out) KDE_FAIL(2, "eval: NULL argument");
   if (!loo && !pos && M > 0) KDE_FAIL(2, "eval: pos is NULL");
-  if (precision != KDEB200_F64 && precision != KDEB200_F32 && precision != KDEB200_F64_BOUNDED)
-    KDE_FAIL(3, "eval: unknown precision %d", precision);
+  if (precision < KDEB200_F64 || precision > KDEB200_F32_BOUNDED) KDE_FAIL(3, "eval: unknown precision %d", precision);
   if (loo) M = bd->N;
   if (M <= 0) return 0;
   // in-process multi-GPU: query rows block-partitioned.  LOO rows are leaf rows: each device returns its block in leaf
   // order and the host scatters through the permutation.  (FP32 LOO has no row-range form: one device.)
-  const bool f32_loo = loo && precision == KDEB200_F32;
+  const bool f32_loo = loo && (precision == KDEB200_F32 || precision == KDEB200_F32_BOUNDED);
   const int G = f32_loo ? 1 : gpus_for(M, 4096);
   std::vector<double> ms(G, 0.0);
   std::vector<int> nl(G, 0);

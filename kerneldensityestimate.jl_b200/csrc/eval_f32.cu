@@ -11,6 +11,7 @@
 #include <cmath>
 #include <vector>
 
+#include "eval_shared.cuh"
 #include "tree.cuh"
 
 namespace kdeb200 {
@@ -39,6 +40,14 @@ struct EvalF32Params {
   int qstride, SE, tile_pairs, loo;
   double ctr[KDEB200_MAX_DIM], scl[KDEB200_MAX_DIM];
   double norm;
+  // error-bounded pruned route (eval_pruned.cu): mask != null => only the tiles of the block's mask row are visited,
+  // CTAs take blocks in `order`, outputs go through qidx (Morton-sorted free queries), rows whose kept sum is below
+  // thresh are listed for the exact FP64 pass
+  const uint32_t *mask, *order, *qidx;
+  int words;
+  double thresh;
+  int64_t *redo;
+  unsigned int *nredo;
 };
 
 template <int D>
@@ -105,18 +114,28 @@ __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_cons
   const int TP = P.tile_pairs;
   const int64_t npairs = (P.N + 1) / 2;
   const int ntiles = (int)((npairs + TP - 1) / TP);
-  auto issue = [&](int t) {
+  const int blk = P.order ? (int)P.order[blockIdx.x] : (int)blockIdx.x;
+  const uint32_t *row = P.mask ? P.mask + (int64_t)blk * P.words : nullptr;
+  auto nxt = [&](int pos) { return row ? next_tile(row, P.words, ntiles, pos) : (pos < ntiles ? pos : ntiles); };
+  auto issue = [&](int t, int slot) {
     const int64_t a = (int64_t)t * TP;
     const int64_t cnt = (npairs - a < TP) ? (npairs - a) : TP;
     const uint32_t bytes = (uint32_t)(cnt * SP * sizeof(float));
-    uint64_t *bar = &bars[t % F32_STAGES];
+    uint64_t *bar = &bars[slot % F32_STAGES];
     mbar_expect_tx(bar, bytes);
-    tma_bulk_g2s(tiles + (size_t)(t % F32_STAGES) * (F32_TILE_BYTES / 4), P.comps + a * SP, bytes, bar);
+    tma_bulk_g2s(tiles + (size_t)(slot % F32_STAGES) * (F32_TILE_BYTES / 4), P.comps + a * SP, bytes, bar);
   };
-  if (tid == 0)
-    for (int t = 0; t < F32_STAGES && t < ntiles; ++t) issue(t);
+  int p_tile = 0, p_slot = 0;  // producer (thread 0): F32_STAGES tiles ahead of the consumers
+  if (tid == 0) {
+    p_tile = nxt(0);
+    while (p_tile < ntiles && p_slot < F32_STAGES) {
+      issue(p_tile, p_slot);
+      ++p_slot;
+      p_tile = nxt(p_tile + 1);
+    }
+  }
 
-  const int64_t qbase = (int64_t)blockIdx.x * (F32_THREADS * Q);
+  const int64_t qbase = (int64_t)blk * (F32_THREADS * Q);
   f32x2 x2[Q][D];  // each query coordinate broadcast into both halves
   double sum[Q];
   int64_t self[Q];
@@ -135,11 +154,12 @@ __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_cons
   }
   const int64_t qlo = qbase, qhi = qbase + F32_THREADS * Q;
 
-  for (int t = 0; t < ntiles; ++t) {
+  int slot = 0;
+  for (int t = nxt(0); t < ntiles; t = nxt(t + 1), ++slot) {
     const int64_t a = (int64_t)t * TP;  // first pair of the tile
     const int cnt = (int)((npairs - a < TP) ? (npairs - a) : TP);
-    mbar_wait(&bars[t % F32_STAGES], (uint32_t)((t / F32_STAGES) & 1));
-    const float *rec = tiles + (size_t)(t % F32_STAGES) * (F32_TILE_BYTES / 4);
+    mbar_wait(&bars[slot % F32_STAGES], (uint32_t)((slot / F32_STAGES) & 1));
+    const float *rec = tiles + (size_t)(slot % F32_STAGES) * (F32_TILE_BYTES / 4);
     const bool check = LOO && (2 * a < qhi) && (2 * (a + cnt) > qlo);
     f32x2 part[Q];
 #pragma unroll
@@ -200,15 +220,25 @@ __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_cons
       sum[i] += (double)plo + (double)phi;
     }
     __syncthreads();
-    if (tid == 0 && t + F32_STAGES < ntiles) issue(t + F32_STAGES);
+    if (tid == 0 && p_tile < ntiles) {
+      issue(p_tile, p_slot);
+      ++p_slot;
+      p_tile = nxt(p_tile + 1);
+    }
   }
 #pragma unroll
   for (int i = 0; i < Q; ++i) {
     const int64_t qi = qbase + tid + (int64_t)i * F32_THREADS;
     if (qi >= P.M) continue;
+    if (P.mask && !(sum[i] >= P.thresh)) {  // too small for the pruning bound: exact FP64 pass (eval_pruned.cu)
+      const unsigned k = atomicAdd(P.nredo, 1u);
+      P.redo[k] = qi;
+      continue;
+    }
     double v = sum[i] / P.norm;
     if (LOO) v = v / (1.0 - P.leafw[qi * P.SE + D]);
-    const int64_t o = (LOO && P.perm) ? P.perm[qi] : qi;
+    int64_t o = (LOO && P.perm) ? P.perm[qi] : qi;
+    if (!LOO && P.qidx) o = P.qidx[qi];
     P.out[o] = v;
   }
 }
@@ -227,8 +257,31 @@ static cudaError_t launch_f32(const EvalF32Params &P, bool loo, unsigned grid, s
   return cudaGetLastError();
 }
 
+// pruned route: the caller (eval_pruned.cu) supplies the mask / order / query map / exact-pass list
+struct F32Prune {
+  const uint32_t *mask = nullptr, *order = nullptr, *qidx = nullptr;
+  int words = 0;
+  double thresh = 0.0;
+  int64_t *redo = nullptr;
+  unsigned int *nredo = nullptr;
+};
+int f32_tile_pairs(int d) {
+  const int SP = (2 * (d + 1) + 3) & ~3;
+  int TP = 1;
+  while (TP * 2 * SP * 4 <= F32_TILE_BYTES) TP *= 2;
+  return TP;
+}
+int f32_queries_per_block() { return F32_THREADS * F32_Q; }
+
+int eval_device_f32_ex(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, double *d_out, cudaStream_t st,
+                       int *launches, const F32Prune *pr);
 int eval_device_f32(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, double *d_out, cudaStream_t st,
                     int *launches) {
+  return eval_device_f32_ex(bd, d_pos, M, loo, d_out, st, launches, nullptr);
+}
+
+int eval_device_f32_ex(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, double *d_out, cudaStream_t st,
+                       int *launches, const F32Prune *pr) {
   if (M <= 0) return 0;
   const int d = bd->d;
   const int SP = (2 * (d + 1) + 3) & ~3;
@@ -272,6 +325,13 @@ int eval_device_f32(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, 
   P.M = M;
   P.loo = loo;
   P.norm = norm;
+  P.mask = pr ? pr->mask : nullptr;
+  P.order = pr ? pr->order : nullptr;
+  P.qidx = pr ? pr->qidx : nullptr;
+  P.words = pr ? pr->words : 0;
+  P.thresh = pr ? pr->thresh : 0.0;
+  P.redo = pr ? pr->redo : nullptr;
+  P.nredo = pr ? pr->nredo : nullptr;
   int TP = 1;
   while (TP * 2 * SP * 4 <= F32_TILE_BYTES) TP *= 2;
   P.tile_pairs = TP;

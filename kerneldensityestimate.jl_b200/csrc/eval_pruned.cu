@@ -161,6 +161,7 @@ struct MaskParams {
   unsigned long long *kept;  // total number of kept (block, tile) pairs (statistics)
   unsigned int *count;       // kept tiles per query block (longest-first launch order)
   int nqb, ntile, words, d;
+  double cut;          // a pair is dropped when 0.5 sum gap^2 / var exceeds this (PR_CUT; the FP32 route uses a smaller one)
   int sym_bq, sym_tn;  // symmetric leave-one-out (sym_bq > 0): rows per block / nodes per tile; tiles that end at or before
                        // the block's first row are dropped (those pairs are produced by the transposed block)
   double half_ivar[KDEB200_MAX_DIM];  // 0.5 / variance_k
@@ -199,7 +200,7 @@ __global__ void mask_kernel(const __grid_constant__ MaskParams P) {
       const double gap = fmax(0.0, fmax(q[k] - c[P.d + k], c[k] - q[P.d + k]));
       acc += gap * gap * P.half_ivar[k];
     }
-    keep = !(acc > PR_CUT);  // NaN boxes are kept
+    keep = !(acc > P.cut);  // NaN boxes are kept
     if (P.sym_bq > 0 && (int64_t)(t + 1) * P.sym_tn <= (int64_t)b * P.sym_bq) keep = false;
   }
   const unsigned bits = __ballot_sync(0xffffffffu, keep);
@@ -223,18 +224,6 @@ struct PrunedParams {
   int64_t *redo;           // list of such rows (position in the block order) ...
   unsigned int *nredo;     // ... and its length
 };
-
-// next set bit at or after position `pos` of the block's mask row; returns ntile when there is none
-__device__ __forceinline__ int next_tile(const uint32_t *__restrict__ row, int words, int ntile, int pos) {
-  int w = pos >> 5;
-  if (w >= words) return ntile;
-  uint32_t bits = row[w] & (0xffffffffu << (pos & 31));
-  while (bits == 0) {
-    if (++w >= words) return ntile;
-    bits = row[w];
-  }
-  return w * 32 + __ffs(bits) - 1;
-}
 
 template <int D, bool LOO>
 __global__ void __launch_bounds__(EV_THREADS) eval_pruned_kernel(const __grid_constant__ PrunedParams P) {
@@ -624,6 +613,7 @@ int eval_pruned_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, int lo
   MP.ntile = ntile;
   MP.words = words;
   MP.d = d;
+  MP.cut = PR_CUT;
   MP.sym_bq = 0;
   MP.sym_tn = 0;
   const int64_t units = (int64_t)nqb * words;
@@ -1068,6 +1058,7 @@ int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStr
   MP.ntile = ntile;
   MP.words = words;
   MP.d = d;
+  MP.cut = PR_CUT;
   MP.sym_bq = bq;
   MP.sym_tn = TN;
   const int64_t units = (int64_t)nrb * words;
@@ -1119,6 +1110,179 @@ int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStr
   KDE_CUDA(cudaGetLastError());
   if (launches) *launches += 6;
   if (int rc = publish_stats(d_kept, d_nredo, (double)nrb * (double)ntile, st)) return rc;
+  KDE_CUDA(cudaFreeAsync(base, st));
+  return 0;
+}
+
+
+// ================================================================ FP32, pruned ================================
+// The FP32 evaluation (eval_f32.cu: packed FADD2 / FFMA2 + MUFU.EX2, contract 1e-5) through the same box-pair pruning.
+// Its tiles hold component PAIRS, so it has its own tile boxes; its bound is looser -- a dropped pair's kernel value is
+// below 1e-16, rows whose kept sum is below 1e10 x that go to the exact pass (FP64, all components) -- so the window is
+// 8.6 instead of 10.9 bandwidths.  Free queries only (the FP32 LOO form has no row-range variant).
+struct F32Prune {
+  const uint32_t *mask = nullptr, *order = nullptr, *qidx = nullptr;
+  int words = 0;
+  double thresh = 0.0;
+  int64_t *redo = nullptr;
+  unsigned int *nredo = nullptr;
+};
+int f32_tile_pairs(int d);
+int f32_queries_per_block();
+int eval_device_f32_ex(kdeb200_tree_t bd, const double *d_pos, int64_t M, int loo, double *d_out, cudaStream_t st,
+                       int *launches, const F32Prune *pr);
+constexpr double PR_CUT32 = 36.84136;  // ln(1e16)
+constexpr double PR_DELTA32 = 1e-16;
+constexpr double PR_REL32 = 1e-6;
+
+int eval_pruned_f32_device(kdeb200_tree_t bd, const double *d_pos, int64_t M, double *d_out, cudaStream_t st, int *launches) {
+  Context &c = ctx();
+  if (M <= 0) return 0;
+  const int d = bd->d, SE = bd->SE;
+  if (M >= (int64_t)1 << 31) KDE_FAIL(3, "eval (pruned): at most 2^31 - 1 query points per call");
+  const int TC = 2 * f32_tile_pairs(d);  // components per FP32 tile
+  const int BQ = f32_queries_per_block();
+  const int ntile = (int)((bd->N + TC - 1) / TC), nqb = (int)((M + BQ - 1) / BQ), words = (ntile + 31) / 32;
+  if (!bd->d_tilebox32) {  // boxes of the pair tiles (cached; the weight total comes from the FP64 boxes or from here)
+    KDE_CUDA(cudaMallocAsync(&bd->d_tilebox32, sizeof(double) * ((size_t)ntile * 2 * d + ntile), c.stream));
+    boxes_kernel<<<(unsigned)((ntile + 3) / 4), 128, 0, c.stream>>>(bd->d_leaf, SE, d, bd->N, TC, bd->d_tilebox32,
+                                                                   bd->d_tilebox32 + (size_t)ntile * 2 * d);
+    KDE_CUDA(cudaGetLastError());
+    std::vector<double> wsum(ntile);
+    KDE_CUDA(cudaMemcpyAsync(wsum.data(), bd->d_tilebox32 + (size_t)ntile * 2 * d, sizeof(double) * ntile, cudaMemcpyDeviceToHost, c.stream));
+    KDE_CUDA(cudaStreamSynchronize(c.stream));
+    double wt = 0.0;
+    for (double w : wsum) wt += std::fabs(w);
+    bd->wtotal = wt;
+    if (launches) *launches += 1;
+  }
+  MaskParams MP;
+  PrunedParams R;  // for the exact FP64 pass
+  EvalParams &E = R.E;
+  E.comps = bd->d_leaf;
+  E.N = bd->N;
+  E.M = M;
+  E.q0 = 0;
+  E.qstride = d;
+  E.perm = nullptr;
+  E.out = d_out;
+  E.partial = nullptr;
+  E.exptab = c.d_exptab;
+  E.ec = make_exp_consts();
+  E.S = 1;
+  E.chunk = 0;
+  E.tile_nodes = TC;
+  double norm = std::pow(2.0 * M_PI, (double)d / 2.0);
+  for (int k = 0; k < d; ++k) {
+    const double v = bd->hvar[k];
+    if (!(v > 0.0) || !std::isfinite(v)) KDE_FAIL(5, "eval: bandwidth variance must be finite and > 0");
+    E.ich[k] = -0.5 / v;
+    MP.half_ivar[k] = 0.5 / v;
+    norm *= std::sqrt(v);
+  }
+  E.norm = norm;
+  const double thresh = PR_DELTA32 * bd->wtotal / PR_REL32;
+
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t b_qbox = up(sizeof(double) * (size_t)nqb * 2 * d), b_mask = up(sizeof(uint32_t) * (size_t)nqb * words),
+               b_redo = up(sizeof(int64_t) * (size_t)M), b_cnt = 256, b_ord = up(sizeof(uint32_t) * (size_t)nqb),
+               b_sorted = up(sizeof(double) * (size_t)M * d), b_keys = up(sizeof(uint64_t) * (size_t)M),
+               b_idx = up(sizeof(uint32_t) * (size_t)M), b_lohi = 256 + sizeof(double) * 2 * KDEB200_MAX_DIM * PR_BOUNDS_BLOCKS;
+  size_t b_otmp = 0, b_tmp = 0;
+  {
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const unsigned int *)nullptr, (unsigned int *)nullptr, (const uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, nqb, 0, 32, st);
+    b_otmp = up(tmp);
+    tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int)M, 0, 64, st);
+    b_tmp = up(tmp);
+  }
+  char *base = nullptr;
+  KDE_CUDA(cudaMallocAsync(&base, b_qbox + b_mask + b_redo + b_cnt + 5 * b_ord + b_otmp + b_sorted + 2 * b_keys + 2 * b_idx + b_tmp + b_lohi, st));
+  char *pp = base;
+  auto take = [&](size_t b) { char *r = pp; pp += b; return r; };
+  double *d_qbox = reinterpret_cast<double *>(take(b_qbox));
+  uint32_t *d_mask = reinterpret_cast<uint32_t *>(take(b_mask));
+  int64_t *d_redo = reinterpret_cast<int64_t *>(take(b_redo));
+  char *d_cnt = take(b_cnt);
+  unsigned int *c_in = reinterpret_cast<unsigned int *>(take(b_ord)), *c_out = reinterpret_cast<unsigned int *>(take(b_ord));
+  uint32_t *o_in = reinterpret_cast<uint32_t *>(take(b_ord)), *o_out = reinterpret_cast<uint32_t *>(take(b_ord));
+  unsigned int *c_key2 = reinterpret_cast<unsigned int *>(take(b_ord));
+  void *d_otmp = take(b_otmp);
+  double *d_sorted = reinterpret_cast<double *>(take(b_sorted));
+  uint64_t *k_in = reinterpret_cast<uint64_t *>(take(b_keys)), *k_out = reinterpret_cast<uint64_t *>(take(b_keys));
+  uint32_t *i_in = reinterpret_cast<uint32_t *>(take(b_idx)), *i_out = reinterpret_cast<uint32_t *>(take(b_idx));
+  void *d_tmp = take(b_tmp);
+  double *d_lohi = reinterpret_cast<double *>(take(b_lohi));
+  unsigned long long *d_kept = reinterpret_cast<unsigned long long *>(d_cnt);
+  unsigned int *d_nredo = reinterpret_cast<unsigned int *>(d_cnt + 16);
+  KDE_CUDA(cudaMemsetAsync(d_cnt, 0, b_cnt, st));
+  KDE_CUDA(cudaMemsetAsync(c_in, 0, b_ord, st));
+  const int bits = 63 / d > 21 ? 21 : 63 / d;
+  bounds_kernel<<<PR_BOUNDS_BLOCKS, 256, 0, st>>>(d_pos, d, M, d_lohi + 32);
+  bounds_final_kernel<<<1, 32, 0, st>>>(d_lohi + 32, PR_BOUNDS_BLOCKS, d, d_lohi);
+  morton_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(d_pos, d, M, d_lohi, bits, k_in, i_in);
+  {
+    size_t tmp = b_tmp;
+    cudaError_t ce = cub::DeviceRadixSort::SortPairs(d_tmp, tmp, k_in, k_out, i_in, i_out, (int)M, 0, bits * d, st);
+    if (ce != cudaSuccess) {
+      cudaFreeAsync(base, st);
+      KDE_FAIL(100 + (int)ce, "eval (pruned, FP32): sorting the query points: %s", cudaGetErrorString(ce));
+    }
+  }
+  gather_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(d_pos, d, M, i_out, d_sorted);
+  boxes_kernel<<<(unsigned)((nqb + 3) / 4), 128, 0, st>>>(d_sorted, d, d, M, BQ, d_qbox, nullptr);
+  KDE_CUDA(cudaGetLastError());
+  MP.qbox = d_qbox;
+  MP.tbox = bd->d_tilebox32;
+  MP.mask = d_mask;
+  MP.kept = d_kept;
+  MP.count = c_in;
+  MP.nqb = nqb;
+  MP.ntile = ntile;
+  MP.words = words;
+  MP.d = d;
+  MP.cut = PR_CUT32;
+  MP.sym_bq = 0;
+  MP.sym_tn = 0;
+  const int64_t units = (int64_t)nqb * words;
+  mask_kernel<<<(unsigned)((units + 3) / 4), 128, 0, st>>>(MP);
+  iota_negate_kernel<<<(unsigned)((nqb + 255) / 256), 256, 0, st>>>(c_in, c_out, o_in, nqb);
+  {
+    size_t tmp = b_otmp;
+    cudaError_t ce = cub::DeviceRadixSort::SortPairs(d_otmp, tmp, c_out, c_key2, o_in, o_out, nqb, 0, 32, st);
+    if (ce != cudaSuccess) {
+      cudaFreeAsync(base, st);
+      KDE_FAIL(100 + (int)ce, "eval (pruned, FP32): ordering the query blocks: %s", cudaGetErrorString(ce));
+    }
+  }
+  F32Prune pr;
+  pr.mask = d_mask;
+  pr.order = o_out;
+  pr.qidx = i_out;
+  pr.words = words;
+  pr.thresh = thresh;
+  pr.redo = d_redo;
+  pr.nredo = d_nredo;
+  if (int rc = eval_device_f32_ex(bd, d_sorted, M, 0, d_out, st, launches, &pr)) {
+    cudaFreeAsync(base, st);
+    return rc;
+  }
+  E.queries = d_sorted;  // the exact pass reads the sorted FP64 queries and writes through the same index map
+  R.mask = d_mask;
+  R.qidx = i_out;
+  R.order = nullptr;
+  R.words = words;
+  R.thresh = thresh;
+  R.redo = d_redo;
+  R.nredo = d_nredo;
+  const unsigned redo_grid = (unsigned)(M < 4 * c.sm_count ? M : 4 * c.sm_count);
+  redo_rows_kernel<<<redo_grid, 256, 0, st>>>(R, d, SE, 0);
+  KDE_CUDA(cudaGetLastError());
+  if (launches) *launches += 9;
+  if (int rc = publish_stats(d_kept, d_nredo, (double)nqb * (double)ntile, st)) return rc;
   KDE_CUDA(cudaFreeAsync(base, st));
   return 0;
 }

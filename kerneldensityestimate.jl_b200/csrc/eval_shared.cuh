@@ -51,6 +51,18 @@ __device__ __forceinline__ double quad(const double (&x)[D], const double (&r)[S
   return acc;
 }
 
+// next set bit at or after position `pos` of the block's mask row; returns ntile when there is none
+__device__ __forceinline__ int next_tile(const uint32_t *__restrict__ row, int words, int ntile, int pos) {
+  int w = pos >> 5;
+  if (w >= words) return ntile;
+  uint32_t bits = row[w] & (0xffffffffu << (pos & 31));
+  while (bits == 0) {
+    if (++w >= words) return ntile;
+    bits = row[w];
+  }
+  return w * 32 + __ffs(bits) - 1;
+}
+
 // Rows whose fast-path total is below EV_TINY (density < 1e-275: the point is > 35 bandwidths away from
 // every component) are recomputed here with libdevice exp, sequentially in leaf order, so that
 // subnormal values and exact zeros (the likelihood's zero rule) match the reference.

@@ -565,6 +565,7 @@ int tree_on(kdeb200_tree_t t, int slot, kdeb200_tree_t *out) {
   r->device = dst.device;
   r->d_leaf32 = nullptr;
   r->d_tilebox = nullptr;
+  r->d_tilebox32 = nullptr;
   r->d_cw = nullptr;
   r->d_leaf_of = nullptr;
   r->slot = slot;
@@ -589,6 +590,7 @@ int tree_destroy(kdeb200_tree_t t) {
   if (t->d_base) cudaFreeAsync(t->d_base, c.stream);
   if (t->d_leaf32) cudaFreeAsync(t->d_leaf32, c.stream);
   if (t->d_tilebox) cudaFreeAsync(t->d_tilebox, c.stream);
+  if (t->d_tilebox32) cudaFreeAsync(t->d_tilebox32, c.stream);
   if (t->d_cw) cudaFreeAsync(t->d_cw, c.stream);
   for (int s = 1; s < KDEB200_MAX_GPUS; ++s)
     if (kdeb200_tree_s *r = t->replica[s]) {
@@ -598,6 +600,7 @@ int tree_destroy(kdeb200_tree_t t) {
         if (r->d_base) cudaFreeAsync(r->d_base, ctx_at(s).stream);
         if (r->d_leaf32) cudaFreeAsync(r->d_leaf32, ctx_at(s).stream);
         if (r->d_tilebox) cudaFreeAsync(r->d_tilebox, ctx_at(s).stream);
+        if (r->d_tilebox32) cudaFreeAsync(r->d_tilebox32, ctx_at(s).stream);
         if (r->d_cw) cudaFreeAsync(r->d_cw, ctx_at(s).stream);
       }
       delete r;

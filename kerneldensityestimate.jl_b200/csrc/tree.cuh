@@ -41,6 +41,7 @@ struct kdeb200_tree_s {
   int64_t *d_perm = nullptr;    // leaf order: original 0-based index
   float *d_leaf32 = nullptr;    // lazily built FP32 shadow of d_leaf (centred, pre-scaled), eval_f32.cu
   double *d_tilebox = nullptr;  // lazily built bounding boxes + weight sums of the component tiles (eval_pruned.cu)
+  double *d_tilebox32 = nullptr;  // ... and of the component-pair tiles of the FP32 kernel
   double wtotal = 0.0;          // sum_i |w_i| (error bound of the pruned evaluation)
   double *d_cw = nullptr;       // lazily built: normalised cumulative weights in ORIGINAL point order (sample, extras.cu)
   int64_t *d_leaf_of = nullptr; // ... and original index -> leaf position (same allocation as d_cw)

@@ -152,3 +152,25 @@ def test_symmetric_loo_likelihood_matches_reference_order_kernel_and_oracle(d, N
     if N <= 20_000:
         o = OKDE.kde_bw(pts, bw, w)
         assert abs(H1 - o.entropy()) <= 1e-12 * abs(H1)
+
+
+@pytest.mark.parametrize("d,N,M", [(1, 30_000, 100_001), (3, 50_000, 80_000), (2, 9_999, 777), (6, 6_000, 5_000)])
+def test_fp32_bounded_eval_within_1e5(d, N, M):
+    """KDEB200_F32_BOUNDED: the packed-FP32 kernel through the box-pair pruning (window 8.6 bandwidths, rows below the
+    bound recomputed in FP64) keeps the FP32 contract of 1e-5 against the FP64 brute-force sum; far queries keep their
+    exact zeros / tiny values through the FP64 exact pass."""
+    rng = np.random.default_rng(7 * d + N)
+    pts, pos = mixture(rng, d, N), mixture(rng, d, M) * 1.05
+    p = K.kde(pts, silverman(pts) * 0.5, rng.random(N) + 0.05)
+    pos[:, :3] = 40.0                                      # hopeless queries: exact pass
+    ref = K.evaluateDualTree(p, pos)
+    got = K.evaluateDualTree(p, pos, precision=K.F32_BOUNDED)
+    kept, redo = K.pruned_stats()
+    assert redo >= 3 and kept < (0.95 if d <= 3 else 1.0001)
+    nz = ref > 1e-300
+    assert relerr(got[nz], ref[nz]) < 1e-5 and np.array_equal(got[~nz] == 0.0, ref[~nz] == 0.0)
+    # leave-one-out calls run the unpruned FP32 kernel: its 1e-5 holds where the sum is not dominated by far-tail terms
+    # (FP32 exponents of ~100 carry ~1e-5 of relative error by themselves)
+    l32, l64 = K.evaluateDualTree(p, p, precision=K.F32_BOUNDED), K.evaluateDualTree(p, p)
+    body = l64 > 1e-3 * np.median(l64)
+    assert body.mean() > 0.9 and relerr(l32[body], l64[body]) < 1e-5
