@@ -401,3 +401,15 @@ def test_full_size_c3_loo_rows_and_kde():
     # and the selected bandwidths sit where theory puts them for this mixture (two modes of sigma 0.6 per dimension,
     # 50k points each: 1.06 sigma n^(-1/5) = 0.073)
     assert np.all(np.abs(bw - 0.073) < 0.012)
+
+
+def test_known_constructions_through_the_gpu_path():
+    """test/testKnownConstructions.jl "should get" comments (tree arrays of test01/02, the whole kde!(3 points) LOOCV
+    result of test03: leaf variance 0.038521) through the library: host builder + device LOOCV."""
+    from tests.test_oracle_golden import check_known_constructions
+
+    def arrays(p):
+        return {"centers": p.bt.centers, "ranges": p.bt.ranges, "weights": p.bt.weights, "means": p.means,
+                "bandwidth": p.bandwidth, "highest_leaf": p.bt.highest_leaf, "lowest_leaf": p.bt.lowest_leaf,
+                "permutation": p.bt.permutation}
+    check_known_constructions(lambda pts, bw, w: K.kde(pts, bw, w), lambda pts: K.kde(pts), arrays)

@@ -72,3 +72,50 @@ def test_disabled_fixture_topology_only(name):
     check_floats(got, exp, case["tol"], [("centers", "centers"), ("ranges", "ranges"), ("weights", "weights"),
                                          ("means", "means")])
     check_inds(got, exp, got["num_points"], INDS)
+
+
+# ---- known answers printed in the reference's test/testKnownConstructions.jl (never asserted there: "should get" comments
+#      from the MATLAB/C++ ancestor).  test01/02 :2-37 -- tree arrays of a 5-point 3-D density; test03 :39-57 -- the whole
+#      kde!(3 points) LOOCV result (leaf variance 0.038521).  test04's 2-D LOOCV comment predates per-dimension bandwidths
+#      (same mismatch as the disabled 2-D lcv fixtures) and pins only topology / centres / ranges.
+KNOWN_T01 = dict(
+    centers=[4.4, 3.6, 5, 3.2, 0.18, 2, 5.5, 6.5, 7.5, 2.6, 0.18, 2.5, 0, 0, 0, 1.9, 1.2, 3, 3.3, -0.81, 2, 4.6, -0.56, 1, 4, 5, 6, 7, 8, 9],
+    weights=[1, 0.6, 0.4, 0.4, 0, 0.2, 0.2, 0.2, 0.2, 0.2],
+    ranges=[2.6, 4.4, 4, 1.4, 0.98, 1, 1.5, 1.5, 1.5, 0.7, 0.98, 0.5] + [0] * 18,
+    highest_leaf=[9, 7, 9, 6, 0, 5, 6, 7, 8, 9], lowest_leaf=[5, 5, 8, 5, 0, 5, 6, 7, 8, 9], permutation=[0, 0, 0, 0, 0, 2, 1, 0, 3, 4])
+KNOWN_T03 = dict(
+    centers=[0.5609, 0.46105, 0, 0.4049, 0.5172, 0.7169], weights=[1, 0.66667, 0, 0.33333, 0.33333, 0.33333],
+    ranges=[0.156, 0.05615, 0, 0, 0, 0], means=[0.54633, 0.46105, 0, 0.4049, 0.5172, 0.7169],
+    bandwidth=[0.05517, 0.041674, 0, 0.038521, 0.038521, 0.038521], permutation=[0, 0, 0, 2, 0, 1])
+
+
+def check_known_constructions(kde_bw, kde_lcv, arrays):
+    """Shared with the gpu suite (tests/test_gpu_eval.py): kde_bw / kde_lcv build the density, arrays(x) returns the
+    reference-named arrays.  0-based ancestor indices: leaves +1, the unused slot stays as the implementation leaves it."""
+    mus = np.array([[4.6173, 3.2641, 1.8729, 4, 7], [-0.5592, -0.8088, 1.1610, 5, 8], [1., 2., 3, 6, 9]])
+    a = arrays(kde_bw(mus, np.sqrt([0.04] * 3), 0.2 * np.ones(5)))
+    used = np.array([i for i in range(10) if i != 4])                 # node 5 (1-based) is the unused slot
+    for k in ("centers", "ranges"):
+        got, exp = np.asarray(a[k]).reshape(10, 3), np.array(KNOWN_T01[k], dtype=float).reshape(10, 3)
+        assert np.all(np.abs(got[used] - exp[used]) <= 0.051 * np.maximum(1.0, np.abs(exp[used]))), k   # 2 printed digits
+    assert np.allclose(np.asarray(a["weights"])[used], np.array(KNOWN_T01["weights"])[used], atol=1e-12)
+    assert np.array_equal(np.asarray(a["highest_leaf"])[used], np.array(KNOWN_T01["highest_leaf"])[used] + 1)
+    assert np.array_equal(np.asarray(a["lowest_leaf"])[used], np.array(KNOWN_T01["lowest_leaf"])[used] + 1)
+    assert np.array_equal(np.asarray(a["permutation"])[5:], np.array(KNOWN_T01["permutation"])[5:] + 1)
+    b = arrays(kde_lcv(np.array([[0.5172, 0.7169, 0.4049]])))          # test03: the LOOCV bandwidth of three points
+    used3 = np.array([0, 1, 3, 4, 5])
+    for k in ("centers", "weights", "ranges", "means", "bandwidth"):
+        got, exp = np.asarray(b[k])[used3], np.array(KNOWN_T03[k])[used3]
+        assert np.all(np.abs(got - exp) <= 6e-5 * np.maximum(np.abs(exp), 0.1)), (k, got, exp)   # 5 printed digits
+    assert np.array_equal(np.asarray(b["permutation"])[3:], np.array(KNOWN_T03["permutation"])[3:] + 1)
+    spls = np.array([[0.5172, 0.7169, 0.4049], [0.0312, 1.0094, 2.0204]])  # test04: topology / centres / ranges only
+    c = arrays(kde_lcv(spls))
+    exp_c = [0.5609, 1.0258, 0.61705, 0.5203, 0, 0, 0.5172, 0.0312, 0.7169, 1.0094, 0.4049, 2.0204]
+    exp_r = [0.156, 0.9946, 0.09985, 0.4891] + [0] * 8
+    assert np.allclose(np.delete(np.asarray(c["centers"]), [4, 5]), np.delete(exp_c, [4, 5]), atol=6e-5)
+    assert np.allclose(np.delete(np.asarray(c["ranges"]), [4, 5]), np.delete(exp_r, [4, 5]), atol=6e-5)
+
+
+def test_oracle_reproduces_known_constructions():
+    from oracle.oracle import OKDE
+    check_known_constructions(OKDE.kde_bw, OKDE.kde_lcv, lambda o: o.arrays())
