@@ -1018,7 +1018,7 @@ int loo_sym_device(kdeb200_tree_t bd, const double *bw_var, double *d_L, cudaStr
   // similar units, longest first
   const int nown = (nrb + nparts - 1) / nparts;
   int nsplit = (8 * 3 * c.sm_count + nown - 1) / nown;
-  if (nsplit > 32) nsplit = 32;
+  if (nsplit > (nparts > 1 ? 64 : 32)) nsplit = nparts > 1 ? 64 : 32;  // a device of a multi-GPU set owns few blocks
   if (nsplit < 1) nsplit = 1;
   const size_t b_row = up(sizeof(double) * (size_t)N * nsplit);
   size_t b_otmp = 0;
