@@ -98,7 +98,7 @@ __global__ void prep_f32_kernel(const double *leaf, int SE, int D, int SP, int64
   for (int k = 2 * (D + 1); k < SP; ++k) out[p * SP + k] = 0.f;
 }
 
-template <int D, bool LOO>
+template <int D, bool LOO, bool PRUNED>
 __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_constant__ EvalF32Params P) {
   constexpr int SP = F32Rec<D>::SP;
   constexpr int Q = F32_Q;
@@ -114,9 +114,9 @@ __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_cons
   const int TP = P.tile_pairs;
   const int64_t npairs = (P.N + 1) / 2;
   const int ntiles = (int)((npairs + TP - 1) / TP);
-  const int blk = P.order ? (int)P.order[blockIdx.x] : (int)blockIdx.x;
-  const uint32_t *row = P.mask ? P.mask + (int64_t)blk * P.words : nullptr;
-  auto nxt = [&](int pos) { return row ? next_tile(row, P.words, ntiles, pos) : (pos < ntiles ? pos : ntiles); };
+  const int blk = PRUNED ? (int)P.order[blockIdx.x] : (int)blockIdx.x;
+  const uint32_t *row = PRUNED ? P.mask + (int64_t)blk * P.words : nullptr;
+  auto nxt = [&](int pos) { return PRUNED ? next_tile(row, P.words, ntiles, pos) : (pos < ntiles ? pos : ntiles); };
   auto issue = [&](int t, int slot) {
     const int64_t a = (int64_t)t * TP;
     const int64_t cnt = (npairs - a < TP) ? (npairs - a) : TP;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_cons
   for (int i = 0; i < Q; ++i) {
     const int64_t qi = qbase + tid + (int64_t)i * F32_THREADS;
     if (qi >= P.M) continue;
-    if (P.mask && !(sum[i] >= P.thresh)) {  // too small for the pruning bound: exact FP64 pass (eval_pruned.cu)
+    if (PRUNED && !(sum[i] >= P.thresh)) {  // too small for the pruning bound: exact FP64 pass (eval_pruned.cu)
       const unsigned k = atomicAdd(P.nredo, 1u);
       P.redo[k] = qi;
       continue;
@@ -238,22 +238,20 @@ __global__ void __launch_bounds__(F32_THREADS) eval_f32_kernel(const __grid_cons
     double v = sum[i] / P.norm;
     if (LOO) v = v / (1.0 - P.leafw[qi * P.SE + D]);
     int64_t o = (LOO && P.perm) ? P.perm[qi] : qi;
-    if (!LOO && P.qidx) o = P.qidx[qi];
+    if (PRUNED && !LOO) o = P.qidx[qi];
     P.out[o] = v;
   }
 }
 
 template <int D>
 static cudaError_t launch_f32(const EvalF32Params &P, bool loo, unsigned grid, size_t smem, cudaStream_t st) {
-  if (loo) {
-    auto k = eval_f32_kernel<D, true>;
+  auto go = [&](auto k) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<grid, F32_THREADS, smem, st>>>(P);
-  } else {
-    auto k = eval_f32_kernel<D, false>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, F32_THREADS, smem, st>>>(P);
-  }
+  };
+  if (P.mask) go(eval_f32_kernel<D, false, true>);  // pruned route: free queries only
+  else if (loo) go(eval_f32_kernel<D, true, false>);
+  else go(eval_f32_kernel<D, false, false>);
   return cudaGetLastError();
 }
 
