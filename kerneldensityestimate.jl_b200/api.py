@@ -406,10 +406,22 @@ def entropy(bd, addop=None, diffop=None):
 
 
 def kld(p1, p2, method="direct"):
-    """src/DualTree01.jl:477-503 (method :direct)"""
-    if method not in ("direct", ":direct"):
-        raise KDEError("kld: only method=:direct is provided")
-    return evalAvgLogL(p1, p1) - evalAvgLogL(p2, p1)
+    """src/DualTree01.jl:477-503: D_KL(p1 || p2) by :direct (p1's own points, leave-one-out for the self term) or
+    :unscented (p1's points plus / minus one bandwidth per dimension, re-fitted by LOOCV; the reference's block indexing
+    (i-1)*N and (2i-1)*N is kept literally, overlaps included)."""
+    if method in ("direct", ":direct"):
+        return evalAvgLogL(p1, p1) - evalAvgLogL(p2, p1)
+    if method in ("unscented", ":unscented"):
+        D, N = Ndim(p1), Npts(p1)
+        ptsE = np.tile(getPoints(p1), (1, 2 * D + 1))
+        bw = getBW(p1)
+        for i in range(1, D + 1):
+            a0, a1 = (i - 1) * N, (2 * i - 1) * N
+            ptsE[i - 1, a0:a0 + N] = ptsE[i - 1, a0:a0 + N] + bw[i - 1, :]
+            ptsE[i - 1, a1:a1 + N] = ptsE[i - 1, a1:a1 + N] - bw[i - 1, :]
+        pE = kde(ptsE)
+        return evalAvgLogL(p1, pE) - evalAvgLogL(p2, pE)
+    raise KDEError("kld: method must be :direct or :unscented")
 
 
 def minkld(p, q):

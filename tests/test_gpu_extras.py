@@ -125,3 +125,25 @@ def test_product_in_one_call_equals_the_two_step_route(d, M, N):
     assert np.array_equal(K.getBW(pq)[:, 0], K.getBW(ref)[:, 0]), (K.getBW(pq)[:, 0], K.getBW(ref)[:, 0])
     o = OKDE.kde_lcv(pts)
     assert relerr(K.getBW(pq)[:, 0] ** 2, o.arrays()["bandwidthMin"][:d]) < 1e-10
+
+
+def test_kld_direct_and_unscented():
+    """kld (src/DualTree01.jl:477-503): both methods, against the oracle assembled the same way."""
+    rng = np.random.default_rng(21)
+    a, b = rng.standard_normal((2, 120)), 0.4 + 1.2 * rng.standard_normal((2, 150))
+    p, q = K.kde(a, [0.4, 0.5]), K.kde(b, [0.5, 0.4])
+    op, oq = OKDE.kde_bw(a, [0.4, 0.5]), OKDE.kde_bw(b, [0.5, 0.4])
+    exp = op.eval_avg_logl(op) - oq.eval_avg_logl(op)
+    assert abs(K.kld(p, q) - exp) <= 1e-11 * abs(exp)
+    D, N = 2, 120
+    ptsE = np.tile(a, (1, 2 * D + 1))
+    bw = np.array([[0.4], [0.5]]) * np.ones((2, N))
+    for i in range(1, D + 1):
+        ptsE[i - 1, (i - 1) * N:(i - 1) * N + N] += bw[i - 1]
+        ptsE[i - 1, (2 * i - 1) * N:(2 * i - 1) * N + N] -= bw[i - 1]
+    oE = OKDE.kde_lcv(ptsE)
+    exp_u = op.eval_avg_logl(oE) - oq.eval_avg_logl(oE)
+    got_u = K.kld(p, q, method="unscented")
+    assert abs(got_u - exp_u) <= 1e-9 * abs(exp_u) and got_u > 0
+    with pytest.raises(K.KDEError):
+        K.kld(p, q, method="nope")
