@@ -55,7 +55,7 @@ struct Schedule {
   int64_t evals = 0;
 };
 
-static void build_schedule(const kdeb200_tree_t *trees, int M, int L, int T, bool masked, Schedule &S) {
+static void build_schedule(const kdeb200_tree_t *trees, int M, int L, int T, bool masked, bool literal, Schedule &S) {
   for (int l = 1; l <= L; ++l) {
     for (int pass = 0; pass <= T; ++pass) {
       for (int j = 0; j < M; ++j) {
@@ -78,7 +78,7 @@ static void build_schedule(const kdeb200_tree_t *trees, int M, int L, int T, boo
           dr.state_stride = t->SA;
           dr.state_has_bw = 0;
         } else {
-          dr.variant = (pass == 0 && !masked) ? VAR_B : VAR_C;
+          dr.variant = (pass == 0 && !masked && !literal) ? VAR_B : VAR_C;  // B records hold -0.5/b, not b
           dr.rec = t->d_buf + (dr.variant == VAR_B ? lv.offB : lv.offC);
           dr.stride = t->SC;
           dr.rec_state = t->d_buf + lv.offC;
@@ -149,7 +149,7 @@ namespace {
 struct SchedEntry {
   uint64_t epoch = 0;
   int slot = 0, M = 0, T = 0;
-  bool masked = false;
+  bool masked = false, literal = false;
   kdeb200_tree_t trees[KDEB200_MAX_DENS] = {nullptr};
   char *d_base = nullptr;  // draws | tiles | counters, one allocation on the context's device
   Draw *d_draws = nullptr;
@@ -176,8 +176,8 @@ void gibbs_drop_schedules(int slot) {
   g_sched[slot].clear();
 }
 
-static int sched_get(const kdeb200_tree_t *trees, int M, int L, int T, bool masked, cudaStream_t st, SchedEntry *out,
-                     int **counter) {
+static int sched_get(const kdeb200_tree_t *trees, int M, int L, int T, bool masked, bool literal, cudaStream_t st,
+                     SchedEntry *out, int **counter) {
   Context &c = ctx();
   std::lock_guard<std::mutex> lk(g_sched_mu);
   auto &lst = g_sched[c.slot];
@@ -191,7 +191,7 @@ static int sched_get(const kdeb200_tree_t *trees, int M, int L, int T, bool mask
     }
   }
   for (auto it = lst.begin(); it != lst.end(); ++it) {
-    if (it->M != M || it->T != T || it->masked != masked) continue;
+    if (it->M != M || it->T != T || it->masked != masked || it->literal != literal) continue;
     bool same = true;
     for (int j = 0; j < M; ++j) same = same && it->trees[j] == trees[j];
     if (!same) continue;
@@ -201,13 +201,14 @@ static int sched_get(const kdeb200_tree_t *trees, int M, int L, int T, bool mask
     return 0;
   }
   Schedule S;
-  build_schedule(trees, M, L, T, masked, S);
+  build_schedule(trees, M, L, T, masked, literal, S);
   SchedEntry e;
   e.epoch = epoch;
   e.slot = c.slot;
   e.M = M;
   e.T = T;
   e.masked = masked;
+  e.literal = literal;
   for (int j = 0; j < M; ++j) e.trees[j] = trees[j];
   e.ndraws = (int)S.draws.size();
   e.ntiles = (int)S.tiles.size();
@@ -258,9 +259,12 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
     if (s1 * perU > nU + 1) KDE_FAIL(7, "gibbs: randU too short (%lld < %lld)", (long long)nU, (long long)(s1 * perU - 1));
     if (s1 * perN > nN) KDE_FAIL(7, "gibbs: randN too short (%lld < %lld)", (long long)nN, (long long)(s1 * perN));
   }
+  // Densities the restructured arithmetic cannot take (zero / non-finite / out-of-range variances, non-finite means or
+  // weights) run through the warp-per-chain kernel with the reference's arithmetic verbatim, NaN / Inf rules included
+  // (src/MSGibbs01.jl:287-315) -- as long as their level lists fit that kernel's shared memory.
+  bool literal = false;
   for (int j = 0; j < ndens; ++j) {
-    if (trees[j]->degenerate)
-      KDE_FAIL(8, "gibbs: density %d has a non-positive, non-finite or out-of-range (variance outside [1e-30, 1e30]) bandwidth/mean; not supported on the GPU path (no CPU fallback)", j + 1);
+    if (trees[j]->degenerate) literal = true;
     if (trees[j]->slot != c.slot) KDE_FAIL(3, "gibbs: tree %d lives on another GPU of the set than the calling context", j);
   }
 
@@ -281,7 +285,8 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
     }
   SchedEntry E;
   int *d_counter = nullptr;
-  if (int rc = sched_get(trees, ndens, L, Niter, masked, st, &E, &d_counter)) return rc;
+  if (literal) masked = true;  // the literal evaluation reads the activity flags in every mode
+  if (int rc = sched_get(trees, ndens, L, Niter, masked, literal, st, &E, &d_counter)) return rc;
 
   P.draws = E.d_draws;
   P.tiles = E.d_tiles;
@@ -304,6 +309,7 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
   P.L = L;
   P.T = Niter;
   P.add_entropy = add_entropy ? 1 : 0;
+  P.literal = literal ? 1 : 0;
   P.nbatches = (int)((s1 - s0 + GB_THREADS - 1) / GB_THREADS);
   for (int j = 0; j < ndens; ++j) {
     const kdeb200_tree_s *t = trees[j];
@@ -322,7 +328,11 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
       if (trees[j]->levels[trees[j]->depth].n > nmax) nmax = (int)trees[j]->levels[trees[j]->depth].n;
     int64_t warp_max = (int64_t)24 * c.sm_count;
     if (const char *ev = getenv("KDEB200_GIBBS_WARP_MAX")) warp_max = atoll(ev);
-    if (s1 - s0 <= warp_max && gibbs_warp_smem(d, nmax) <= 96 * 1024) {
+    if (literal && gibbs_warp_smem(d, nmax) > 96 * 1024)
+      KDE_FAIL(8, "gibbs: a density has a zero, non-finite or out-of-range (variance outside [1e-30, 1e30]) bandwidth / mean / "
+                  "weight and more than ~2900 components: the verbatim-arithmetic kernel cannot hold its level lists "
+                  "(no CPU fallback)");
+    if ((literal || s1 - s0 <= warp_max) && gibbs_warp_smem(d, nmax) <= 96 * 1024) {
       cudaError_t we = cudaErrorInvalidValue;
       switch (d) {
 #ifdef GB_ONLY_D3

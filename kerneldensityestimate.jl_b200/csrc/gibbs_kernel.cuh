@@ -104,6 +104,7 @@ struct GibbsParams {
   int64_t s0, s1, perU, perN;
   uint64_t seed;
   int ndraws, ntiles, M, L, T, add_entropy, nbatches;
+  int literal;  // K1w only: the reference's arithmetic verbatim (divide, log, NaN rules) for degenerate bandwidths
   const double *root_rec[KDEB200_MAX_DENS];  // [m.., b.., lnw] of node 1
   const int64_t *labels[KDEB200_MAX_DENS];   // deepest level: permutation + 1
   double hvar[KDEB200_MAX_DENS][KDEB200_MAX_DIM];
@@ -674,6 +675,30 @@ cudaError_t launch_gibbs_d(const GibbsParams &P, bool masked, int grid_cap, size
 // used when the call has too few chains for the thread-per-chain kernel (gibbs.cu picks).
 constexpr int GW_WARPS = 4;  // chains per CTA
 
+// makeFasterSampleIndex! verbatim (src/MSGibbs01.jl:287-303) for one node: per active dimension
+//   distr = (mean - mu)^2 / c;  if !isnan(distr): acc += distr; acc += log(c)      p = exp(-0.5 acc) * w;  NaN -> 0
+// Used for densities the restructured arithmetic cannot take (zero / huge / non-finite variances): IEEE divides and
+// libdevice log / exp produce the Inf / NaN pattern the reference's rules are written for.
+template <int D, bool MASK>
+__device__ __forceinline__ double eval_node_literal(const double *__restrict__ r, bool has_bw, const double *__restrict__ hvar,
+                                                    const Hoist<D, MASK> &h, double w) {
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    if (!h.act[k]) continue;
+    const double c = __dadd_rn(has_bw ? __ldg(r + D + k) : hvar[k], h.cadd[k]);
+    const double m = __dadd_rn(__ldg(r + k), -h.mu[k]);
+    const double distr = __ddiv_rn(__dmul_rn(m, m), c);
+    if (!isnan(distr)) {
+      acc = __dadd_rn(acc, distr);
+      acc = __dadd_rn(acc, log(c));
+    }
+  }
+  double p = __dmul_rn(exp(__dmul_rn(-0.5, acc)), w);
+  if (isnan(p)) p = 0.0;
+  return p;
+}
+
 template <int D, bool MASK>
 __global__ void __launch_bounds__(GW_WARPS * 32) gibbs_warp_kernel(const __grid_constant__ GibbsParams P, int nmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -776,7 +801,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32) gibbs_warp_kernel(const __grid_
         const double c = __shfl_sync(FULL, c_k, k);
         if (!MASK || h.act[k]) prod *= c;  // same order of multiplications as gibbs_kernel
       }
-      if (dr.variant == VAR_A) scale = kde_rsqrt(prod);
+      if (dr.variant == VAR_A && !P.literal) scale = kde_rsqrt(prod);
     }
 
     // pass 1, parallel part: p[z]
@@ -784,7 +809,8 @@ __global__ void __launch_bounds__(GW_WARPS * 32) gibbs_warp_kernel(const __grid_
     for (int z = lane; z < n; z += 32) {
       const double *r = dr.rec + (size_t)z * dr.stride;
       double p;
-      if (dr.variant == VAR_A) p = eval_node<D, MASK, VAR_A, true>(r, h, tab, P.ec);
+      if (P.literal) p = eval_node_literal<D, MASK>(r, dr.variant != VAR_A, P.hvar[j], h, __ldg(dr.wts + z));
+      else if (dr.variant == VAR_A) p = eval_node<D, MASK, VAR_A, true>(r, h, tab, P.ec);
       else if (dr.variant == VAR_B) p = eval_node<D, MASK, VAR_B, true>(r, h, tab, P.ec);
       else p = eval_node<D, MASK, VAR_C, true>(r, h, tab, P.ec);
       pbuf[z] = p;
@@ -792,7 +818,29 @@ __global__ void __launch_bounds__(GW_WARPS * 32) gibbs_warp_kernel(const __grid_
     __syncwarp();
     // pass 1, sequential part: running sums in node order (one lane; 4 loads in flight ahead of the adds)
     double pT = 0.0;
-    if (lane == 0) {
+    if (P.literal) {
+      // :305-327 verbatim: pT, the pT < 1e-99 rule, p[z] /= pT, running sum -- so that Inf / NaN totals select what the
+      // reference's comparisons `randU <= p[z]` select (a NaN entry is never chosen, the walk ends on the last node)
+      if (lane == 0) {
+        double S = 0.0;
+        for (int z = 0; z < n; ++z) S = __dadd_rn(S, pbuf[z]);
+        if (S < 1e-99) {
+          const double w = dr.wts[n - 1];
+          S = 0.0;
+          for (int z = 0; z < n; ++z) {
+            pbuf[z] = w;
+            S = __dadd_rn(S, w);
+          }
+        }
+        double c = 0.0;
+        for (int z = 0; z < n; ++z) {
+          const double q = __ddiv_rn(pbuf[z], S);
+          c = z ? __dadd_rn(q, c) : q;
+          pbuf[z] = c;
+        }
+      }
+      pT = 1.0;  // the search below compares u itself with the normalised running sums
+    } else if (lane == 0) {
       double S = 0.0;
       int z = 0;
       for (; z + 4 <= n; z += 4) {
@@ -837,7 +885,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32) gibbs_warp_kernel(const __grid_
       } else {
         const double target = u * pT;
         unsigned best = (unsigned)(n - 1);
-        for (int z = lane; z < n; z += 32)
+        for (int z = lane; z < n - 1; z += 32)
           if (target <= pbuf[z]) {
             best = (unsigned)z;
             break;

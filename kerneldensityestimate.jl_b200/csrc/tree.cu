@@ -359,7 +359,7 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
   for (int k = 0; k < d; ++k) t->root_mean[k] = means[k];
   for (int64_t i = N; i < NN; ++i)
     for (int k = 0; k < d; ++k)
-      if (bandwidth[i * d + k] != t->hvar[k]) {
+      if (bandwidth[i * d + k] != t->hvar[k] && !(std::isnan(bandwidth[i * d + k]) && std::isnan(t->hvar[k]))) {
         delete t;
         KDE_FAIL(4, "tree_create: per-point bandwidths (multibandwidth != 0) are not supported");
       }

@@ -329,3 +329,40 @@ def test_very_large_trees_multi_tile_chunks():
     rng = np.random.default_rng(31337)
     pairs = [make(rng, 2, 100_000, 0.25 * j) for j in range(2)]
     compare([p[0] for p in pairs], [p[1] for p in pairs], 130, 1, rng)
+
+
+DEGENERATE_BW = {
+    "zero_in_one_dim": [[0.3, 0.3], [0.0, 0.3], [0.3, 0.3]],
+    "zero_everywhere": [[0.0, 0.0], [0.3, 0.3], [0.3, 0.3]],
+    "nan_in_one_dim": [[np.nan, 0.3], [0.3, 0.3], [0.3, 0.3]],
+    "inf_in_one_dim": [[np.inf, 0.3], [0.3, 0.3], [0.3, 0.3]],
+    "variance_1e50": [[1e25, 0.3], [0.3, 0.3], [0.3, 0.3]],
+    "variance_1e-50": [[1e-25, 0.3], [0.3, 0.3], [1e-25, 1e-25]],
+}
+
+
+@pytest.mark.parametrize("case", sorted(DEGENERATE_BW))
+def test_degenerate_bandwidths_follow_the_reference_nan_rules(case):
+    """zero / NaN / Inf / out-of-range bandwidths used to be refused (code 8); the reference skips NaN
+    terms, zeroes NaN likelihoods and falls back to the last node's weight (src/MSGibbs01.jl:287-315).  The library now runs
+    such products through the verbatim-arithmetic variant of the warp-per-chain kernel (whatever the chain count): labels
+    identical to the oracle, points identical including where they are NaN."""
+    rng = np.random.default_rng(77)
+    d, N, Np, T = 2, 60, 150, 3
+    kt, ot = [], []
+    for j, bw in enumerate(DEGENERATE_BW[case]):
+        pts = mixture(rng, d, N, 0.25 * j)
+        kt.append(K.kde(pts, bw))
+        ot.append(O.OKDE.kde_bw(pts, bw))
+    nU, nN = O.prod_sizes(ot, Np, T)
+    U, G = rng.random(nU), rng.standard_normal(nN)
+    with np.errstate(all="ignore"):
+        epts, eind = O.gibbs(ot, Np, T, U, G)
+    gpts, gind = K.prodAppxMSGibbsS(None, kt, None, None, Niter=T, Np=Np, randU=U, randN=G)
+    assert np.array_equal(gind, eind)
+    assert np.array_equal(np.isnan(gpts), np.isnan(epts)) and np.array_equal(np.isinf(gpts), np.isinf(epts))
+    fin = np.isfinite(epts)
+    if fin.any():
+        assert np.max(np.abs(gpts[fin] - epts[fin]) / np.maximum(np.abs(epts[fin]), 1e-3)) < PT_TOL
+    if case.startswith("variance"):
+        assert fin.all()  # out-of-range but finite: ordinary results, only the arithmetic route differs
