@@ -124,6 +124,17 @@ int kdeb200_gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int
 int kdeb200_product_kde(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, int add_entropy,
                         const uint8_t *dimmask, uint64_t seed, double *points_out, int64_t *indices_out,
                         double *bw_std_out, int *nloo_calls_out);
+/* Arithmetic of the label probabilities in kdeb200_gibbs / _gibbs_device / _product_kde (process-wide; default KDEB200_F64;
+ * the environment variable KDEB200_GIBBS_F32=1/0 overrides):
+ *   KDEB200_F64  parity mode (a): labels identical to the reference under injected variates.
+ *   KDEB200_F32  statistical mode (b) only: makeFasterSampleIndex! (src/MSGibbs01.jl:250-328) evaluated in packed FP32
+ *                with MUFU ex2 / rsqrt (2^-22 relative per term) on calls large enough for the thread-per-chain kernel;
+ *                chain state, samplePoint! and the output points stay FP64.  With the same seed a chain follows the FP64
+ *                kernel until a uniform lands within ~1e-6 of a CDF edge.  A draw whose FP32 total under/overflows is
+ *                redone in FP64 with the reference's literal arithmetic (kdeb200_gibbs_f32_slow_draws counts them since
+ *                its last call).  Refused (code 8) when a bandwidth is below 1e-4 of the data spread. */
+int kdeb200_set_gibbs_precision(int precision);
+int kdeb200_gibbs_f32_slow_draws(unsigned long long *count_out);
 /* glbs.Nlevels (src/MSGibbs01.jl:555-568) and the per-sample stream consumption. */
 int kdeb200_gibbs_sizes(const kdeb200_tree_t *trees, int ndens, int Niter, int *nlevels,
                         int64_t *uniforms_per_sample, int64_t *normals_per_sample,

@@ -54,6 +54,8 @@ SIGNATURES = {
     "kdeb200_eval_marginals": (C.c_int, [tree_t, f64p, C.c_int64, f64p]),
     "kdeb200_sample": (C.c_int, [tree_t, C.c_int64, C.c_uint64, f64p, f64p, f64p, i64p]),
     "kdeb200_set_pruning": (C.c_int, [C.c_int]),
+    "kdeb200_set_gibbs_precision": (C.c_int, [C.c_int]),
+    "kdeb200_gibbs_f32_slow_draws": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "kdeb200_pruned_stats": (C.c_int, [f64p, i64p]),
     "kdeb200_pipe_peak": (C.c_int, [C.c_int, C.c_int, f64p, f64p]),
     "kdeb200_dfma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, f64p]),

@@ -29,7 +29,7 @@ __all__ = [
     "KDEError", "BallTree", "BallTreeDensity", "kde", "kde_bang", "getPoints", "getBW", "getWeights", "marginal",
     "sample", "rand", "resample", "evaluateDualTree", "evalAvgLogL", "entropy", "kld", "minkld", "nLOO_LL", "golden",
     "ksize", "neighborMinMax", "lcv_bandwidths", "updateBandwidth", "prodAppxMSGibbsS", "Ndim", "Npts", "init", "init_multi", "multi_count", "gibbs_sizes",
-    "philox_streams", "pipe_peak", "last_kernel_ms", "F64", "F32", "F64_BOUNDED", "F32_BOUNDED", "setForceEvalDirect", "set_pruning", "pruned_stats", "prod", "getKDERange", "getKDERangeLinspace",
+    "philox_streams", "pipe_peak", "last_kernel_ms", "F64", "F32", "F64_BOUNDED", "F32_BOUNDED", "setForceEvalDirect", "set_pruning", "set_gibbs_precision", "gibbs_f32_slow_draws", "pruned_stats", "prod", "getKDERange", "getKDERangeLinspace",
     "getKDEMax", "getKDEMean", "getKDEfit", "intersIntgAppxIS", "eval_marginals", "to_string", "from_string",
 ]
 
@@ -70,6 +70,19 @@ def setForceEvalDirect(flag):
 def set_pruning(mode):
     """kdeb200_set_pruning: 0 brute force everywhere, 1 (default) pruned LOO likelihood only, 2 pruned evaluations too."""
     check(lib().kdeb200_set_pruning(int(mode)))
+
+
+def set_gibbs_precision(precision):
+    """kdeb200_set_gibbs_precision: F64 (default, parity mode: labels exact under injected variates) or F32 (statistical
+    mode only: label probabilities in packed FP32 on calls large enough for the thread-per-chain kernel)."""
+    check(lib().kdeb200_set_gibbs_precision(int(precision)))
+
+
+def gibbs_f32_slow_draws():
+    """label draws the FP32 sampler redid in FP64 (its FP32 total under/overflowed) since the last call"""
+    n = C.c_ulonglong(0)
+    check(lib().kdeb200_gibbs_f32_slow_draws(C.byref(n)))
+    return int(n.value)
 
 
 def pruned_stats():

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkdeb200.so")
-SOURCES = ["context.cu", "tree.cu", "eval.cu", "eval_pruned.cu", "eval_f32.cu", "extras.cu", "lcv.cu", "gibbs.cu", "peaks.cu", "capi.cu"] + [
+SOURCES = ["context.cu", "tree.cu", "eval.cu", "eval_pruned.cu", "eval_f32.cu", "extras.cu", "lcv.cu", "gibbs.cu", "gibbs_f32.cu", "peaks.cu", "capi.cu"] + [
     "gibbs_d%d.cu" % d for d in range(1, 9)]
 GIBBS_TUNED = ["gibbs.cu", "gibbs_d3.cu"]  # what the tuning variants rebuild (GB_ONLY_D3)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -23,6 +23,7 @@ KERNEL_SOURCES = {
     "eval_pruned": ["eval_pruned.cu", "eval_shared.cuh", "common.cuh"],
     "eval_f32": ["eval_f32.cu", "common.cuh"],
     "lcv": ["lcv.cu", "eval_shared.cuh", "common.cuh"],
+    "gibbs_f32": ["gibbs_f32.cu", "gibbs_kernel.cuh", "common.cuh"],
 }
 
 

@@ -49,6 +49,8 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
                  int64_t *d_level_labels, cudaStream_t st, int *launches);
 int philox_streams_device(uint64_t seed, int64_t Np, int64_t perU, int64_t perN, double *d_U, double *d_G,
                           cudaStream_t st);
+int gibbs_set_precision(int p);
+int gibbs32_slow_draws(unsigned long long *out);
 int pipe_peak(int which, int iters, double *lane_ops_per_s, double *ms_out);
 int dfma_probe(int ilp, int blocks_per_sm, int threads, int iters, double *lane_ops_per_s);
 
@@ -605,6 +607,18 @@ int kdeb200_set_pruning(int mode) {
   if (mode < 0 || mode > 2) KDE_FAIL(3, "set_pruning: mode must be 0, 1 or 2");
   set_prune_mode(mode);
   return 0;
+}
+
+int kdeb200_set_gibbs_precision(int precision) {
+  KDE_SERIALISE();
+  return gibbs_set_precision(precision);
+}
+
+int kdeb200_gibbs_f32_slow_draws(unsigned long long *count_out) {
+  KDE_SERIALISE();
+  if (!count_out) KDE_FAIL(2, "gibbs_f32_slow_draws: NULL argument");
+  if (int rc = ensure_init()) return rc;
+  return gibbs32_slow_draws(count_out);
 }
 
 int kdeb200_pruned_stats(double *kept_fraction, int64_t *redo_rows) {

@@ -12,6 +12,11 @@
 
 namespace kdeb200 {
 
+// gibbs_f32.cu
+int gibbs_precision();
+void gibbs32_drop_schedules(int slot);
+int gibbs32_launch(const kdeb200_tree_t *trees, int ndens, int L, int Niter, bool masked, GibbsParams &P, cudaStream_t st);
+
 extern template cudaError_t launch_gibbs_d<1>(const GibbsParams &, bool, int, size_t, cudaStream_t, int);
 extern template cudaError_t launch_gibbs_d<2>(const GibbsParams &, bool, int, size_t, cudaStream_t, int);
 extern template cudaError_t launch_gibbs_d<3>(const GibbsParams &, bool, int, size_t, cudaStream_t, int);
@@ -171,6 +176,7 @@ void sched_free(SchedEntry &e, cudaStream_t st) {
 
 // drops every cached schedule of a context (its device memory is about to go away)
 void gibbs_drop_schedules(int slot) {
+  gibbs32_drop_schedules(slot);
   std::lock_guard<std::mutex> lk(g_sched_mu);
   for (auto &e : g_sched[slot]) sched_free(e, ctx_at(slot).stream);
   g_sched[slot].clear();
@@ -352,6 +358,11 @@ int gibbs_device(const kdeb200_tree_t *trees, int ndens, int64_t Np, int Niter, 
       if (launches) *launches += 1;
       return 0;
     }
+  }
+  if (gibbs_precision() == KDEB200_F32) {  // K1f: FP32 label probabilities (statistical mode only), gibbs_f32.cu
+    if (int rc = gibbs32_launch(trees, ndens, L, Niter, masked, P, st)) return rc;
+    if (launches) *launches += 1;
+    return 0;
   }
   const size_t smem = GB_STAGES * GB_TILE_BYTES;
   cudaError_t e = cudaErrorInvalidValue;

@@ -110,6 +110,9 @@ struct GibbsParams {
   double hvar[KDEB200_MAX_DENS][KDEB200_MAX_DIM];
   unsigned char mask[KDEB200_MAX_DENS][KDEB200_MAX_DIM];   // partialDimMask[j][k]
   unsigned char other[KDEB200_MAX_DENS][KDEB200_MAX_DIM];  // OR_{i != j} mask[i][k]
+  // K1f (gibbs_f32.cu) only: the affine map of its FP32 records, x' = (x - nctr) * nisig, and the slow-draw counter
+  double nctr[KDEB200_MAX_DIM], nisig[KDEB200_MAX_DIM];
+  unsigned long long *slow_draws;
 };
 
 // ---- one kernel evaluation, three record layouts -----------------------------------------

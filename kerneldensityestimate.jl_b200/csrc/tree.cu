@@ -357,6 +357,7 @@ int tree_create(int d, int64_t N, const double *means, const double *bandwidth, 
   // uniform leaf bandwidth is what the typed constructors of the reference always produce
   for (int k = 0; k < d; ++k) t->hvar[k] = bandwidth[N * d + k];
   for (int k = 0; k < d; ++k) t->root_mean[k] = means[k];
+  for (int k = 0; k < d; ++k) t->root_var[k] = bandwidth[k];
   for (int64_t i = N; i < NN; ++i)
     for (int k = 0; k < d; ++k)
       if (bandwidth[i * d + k] != t->hvar[k] && !(std::isnan(bandwidth[i * d + k]) && std::isnan(t->hvar[k]))) {

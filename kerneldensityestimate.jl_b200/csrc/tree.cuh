@@ -28,6 +28,7 @@ struct kdeb200_tree_s {
   bool degenerate = false;  // some bandwidth <= 0 or non-finite value: fast arithmetic not valid
   double hvar[KDEB200_MAX_DIM] = {0};  // the uniform leaf variances (bandwidthMin/Max[1:d])
   double root_mean[KDEB200_MAX_DIM] = {0};  // mean of node 1 (centre of the FP32 coordinates)
+  double root_var[KDEB200_MAX_DIM] = {0};   // bandwidth (variance) of node 1: data spread + leaf bandwidth (FP32 Gibbs map)
   double extent[KDEB200_MAX_DIM] = {0};     // max_i |x_i - root_mean| per dimension (FP32 accuracy guard)
   int SA = 0, SC = 0, SE = 0;          // record strides in doubles (even => 16-byte aligned records)
   std::vector<kdeb200::Level> levels;  // levels[0] = {root}; levels[l], l = 1..depth
