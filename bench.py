@@ -562,6 +562,52 @@ def main():
     e2e_val = e2e_n * world / e2e_dt
     handles = _api._handles(trees)  # the e2e leg rebuilt the device trees
 
+    # ---- K1f: the same call with the label probabilities in packed FP32 (statistical mode (b) only; NOT the headline:
+    # labels are not bit-exact against the reference).  MUFU-pipe roofline: 1 ex2 per leaf-level / sampleIndices! node,
+    # rsqrt + ex2 per internal sampleIndex node (SURVEY.md 8d "FP32 variant").
+    c4_f32 = None
+    if not args.no_secondary and world == 1 and rank == 0:
+        nchk = min(65536, n_per)
+        st = torch.cuda.current_stream().cuda_stream
+        K.set_gibbs_precision(K.F32)
+        try:
+            fms = []
+            for i in range(4):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _lib.check(L.kdeb200_gibbs_device(handles, NDENS, Np_total, NITER, 1, None, None, 0, None, 0, SEED, s0, s1,
+                                                  d_pts.data_ptr(), d_idx.data_ptr(), None, st))
+                b.record()
+                torch.cuda.synchronize()
+                if i > 0:
+                    fms.append(a.elapsed_time(b))
+            p32, i32 = d_pts[:nchk].clone(), d_idx[:nchk].clone()
+            slow = K.gibbs_f32_slow_draws()
+        finally:
+            K.set_gibbs_precision(K.F64)
+        _lib.check(L.kdeb200_gibbs_device(handles, NDENS, Np_total, NITER, 1, None, None, 0, None, 0, SEED, s0, s0 + nchk,
+                                          d_pts.data_ptr(), d_idx.data_ptr(), None, st))
+        torch.cuda.synchronize()
+        same = (d_idx[:nchk] == i32).all(dim=1)
+        f_ms = float(np.mean(fms))
+        mufu0, _ = K.pipe_peak(2, 200000)
+        leaf = NDENS * 2 * NCOMP * (1 + NITER)
+        internal = evals - leaf
+        mufu_per_sample = leaf + internal * (NITER * 2 + 1) / (1.0 + NITER)
+        c4_f32 = {"workload": "C4 with kdeb200_set_gibbs_precision(KDEB200_F32): same trees, seed and sample range as the headline",
+                  "value": n_per / (f_ms * 1e-3), "unit": "samples/s", "kernel_ms": f_ms, "dtype": "f32 label probabilities, f64 chain state and points",
+                  "parity": "statistical (mode b): fraction of samples whose 8 labels equal the FP64 kernel's under the same Philox streams",
+                  "same_labels_as_f64": float(same.float().mean().item()), "samples_compared": nchk,
+                  "max_point_diff_where_labels_agree": float((d_pts[:nchk][same] - p32[same]).abs().max().item()) if bool(same.any()) else None,
+                  "draws_redone_in_fp64": slow, "speedup_vs_f64_kernel": k_ms / f_ms,
+                  "roofline": {"bound": "mufu (ex2 / rsqrt)", "mufu_lane_ops_per_sample": mufu_per_sample,
+                               "achieved": mufu_per_sample * n_per / (f_ms * 1e-3) / 1e12, "peak": mufu0 / 1e12, "unit": "T MUFU/s",
+                               "frac": mufu_per_sample * n_per / (f_ms * 1e-3) / mufu0, "kernel": "gibbs_f32_kernel<3,8>",
+                               "peak_source": "MUFU.EX2 microbenchmark (kdeb200_pipe_peak) in this run",
+                               "note": "ncu (profiles/r02_gibbs_f32_ncu.txt): issue slots 61 %, XU pipe ~58 %, LSU data pipe ~75 % busy -- "
+                                       "no single pipe saturated; see DESIGN.md K1f"}}
+
     secondary = None
     if not args.no_secondary:
         if world > 1:
@@ -570,6 +616,7 @@ def main():
             dfma0, _ = K.pipe_peak(0, 200000)
             mufu0, _ = K.pipe_peak(2, 200000)
             secondary = secondary_single(K, dfma0, mufu0, args)
+            secondary["c4_f32"] = c4_f32
 
     if rank == 0:
         # roofline denominators measured live: dependency-free DFMA stream

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkdeb200.so")
 SOURCES = ["context.cu", "tree.cu", "eval.cu", "eval_pruned.cu", "eval_f32.cu", "extras.cu", "lcv.cu", "gibbs.cu", "gibbs_f32.cu", "peaks.cu", "capi.cu"] + [
-    "gibbs_d%d.cu" % d for d in range(1, 9)]
+    "gibbs_d%d.cu" % d for d in range(1, 9)] + ["gibbs_f32_d%d.cu" % d for d in range(1, 9)]
 GIBBS_TUNED = ["gibbs.cu", "gibbs_d3.cu"]  # what the tuning variants rebuild (GB_ONLY_D3)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -23,7 +23,7 @@ KERNEL_SOURCES = {
     "eval_pruned": ["eval_pruned.cu", "eval_shared.cuh", "common.cuh"],
     "eval_f32": ["eval_f32.cu", "common.cuh"],
     "lcv": ["lcv.cu", "eval_shared.cuh", "common.cuh"],
-    "gibbs_f32": ["gibbs_f32.cu", "gibbs_kernel.cuh", "common.cuh"],
+    "gibbs_f32": ["gibbs_f32_kernel.cuh", "gibbs_f32.cu", "gibbs_kernel.cuh", "common.cuh"],
 }
 
 
@@ -66,7 +66,8 @@ def _build_variant(tag, defines):
     build()
     for s in SOURCES:
         if s not in GIBBS_TUNED:  # everything else comes from the main build
-            if not (s.startswith("gibbs_d") and any("GB_ONLY_D3" in d for d in defines)):
+            if not (s.startswith("gibbs_d") and any("GB_ONLY_D3" in d for d in defines)) and not (
+                    s.startswith("gibbs_f32_d") and s != "gibbs_f32_d3.cu" and any("GF_ONLY_D3" in d for d in defines)):
                 objs.append(os.path.join(HERE, "build", s.replace(".cu", ".o")))
             continue
         o = os.path.join(bdir, s.replace(".cu", ".o"))

@@ -1,0 +1,5 @@
+// gibbs_f32_d8.cu -- explicit instantiation of the FP32 Gibbs kernel for d = 8.
+#include "gibbs_f32_kernel.cuh"
+namespace kdeb200 {
+template cudaError_t launch_gibbs_f32_d<8>(const GibbsParams &, int, size_t, cudaStream_t, int);
+}

@@ -56,6 +56,9 @@ for s in specs:
          "dram_read_bytes": to_bytes(*m["dram__bytes_read.sum"]), "dram_write_bytes": to_bytes(*m["dram__bytes_write.sum"]),
          "duration_ns": to_ns(*m["gpu__time_duration.sum"]),
          "fp64_pipe_active_pct": m["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"][1], "csv": os.path.basename(path)}
+    if "smsp__inst_executed_pipe_xu.sum" in m:  # MUFU / conversions (the FP32 Gibbs kernel's bound)
+        e["xu_warp_instr"] = m["smsp__inst_executed_pipe_xu.sum"][1]
+        e["xu_lane_instr_per_unit"] = e["xu_warp_instr"] * 32 / units
     e["fp64_lane_instr_per_unit"] = e["fp64_warp_instr"] * 32 / units
     e["other_lane_instr_per_unit"] = (e["warp_instr"] - e["fp64_warp_instr"]) * 32 / units
     e["dram_bytes_per_unit"] = (e["dram_read_bytes"] + e["dram_write_bytes"]) / units
