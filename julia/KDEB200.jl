@@ -37,6 +37,15 @@ end
 # (every value within 1e-13 of the brute-force sum; the reference's dual tree: errTol = 1e-3) for evaluate!
 setForceEvalDirect!(flag::Bool) = check(ccall((:kdeb200_set_pruning, LIB), Cint, (Cint,), flag ? 1 : 2))
 
+# Arithmetic of the Gibbs label probabilities: 0 = FP64 (default; labels identical to the reference under injected
+# randU / randN), 1 = packed FP32 on large calls (free-running statistical mode only, ~3x the sample rate)
+set_gibbs_precision!(precision::Int) = check(ccall((:kdeb200_set_gibbs_precision, LIB), Cint, (Cint,), precision))
+function gibbs_f32_slow_draws()
+  n = Ref{Culonglong}(0)
+  check(ccall((:kdeb200_gibbs_f32_slow_draws, LIB), Cint, (Ref{Culonglong},), n))
+  return Int(n[])
+end
+
 # ---- S0: device-resident BallTreeDensity -------------------------------------------------
 mutable struct DeviceTree
   h::Ptr{Cvoid}
