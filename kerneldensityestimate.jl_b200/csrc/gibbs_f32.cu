@@ -198,6 +198,7 @@ static int s32_get(const kdeb200_tree_t *trees, int M, int L, int T, bool masked
     pd.dst_stride = gf_stride(d, var);
     const size_t off = nfloats;
     nfloats += (size_t)((lv.n + 1) / 2) * pd.dst_stride;
+    nfloats = (nfloats + 7) & ~(size_t)7;  // 32-byte aligned blocks: pass 2 reads them with 256-bit loads
     preps.push_back(pd);
     prep_off.push_back(off);
     block[key] = off;

@@ -108,6 +108,17 @@ __device__ __forceinline__ void gf_load(const float *__restrict__ r, f32x2 (&v)[
     return;
   }
 #endif
+  if (NC && S % 8 == 0) {
+    // pass 2: every lane reads ITS OWN chunk, so a warp-wide load touches 32 different lines and its cost in the LSU data
+    // pipe is per instruction: one 256-bit load (LDG.E.ENL2.256, sm_100) instead of two 128-bit ones per 32 bytes
+#pragma unroll
+    for (int k = 0; k < S / 8; ++k) {
+      asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];"
+                   : "=l"(v[4 * k]), "=l"(v[4 * k + 1]), "=l"(v[4 * k + 2]), "=l"(v[4 * k + 3])
+                   : "l"(r + 8 * k));
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < S / 4; ++k) {
     const ulonglong2 q = NC ? __ldg(reinterpret_cast<const ulonglong2 *>(r) + k) : reinterpret_cast<const ulonglong2 *>(r)[k];
@@ -371,6 +382,7 @@ __global__ void __launch_bounds__(GB_THREADS, gf_minblocks(D)) gibbs_f32_kernel(
   R.known = (batch < P.nbatches) ? P.ntiles : 0;
   R.issued = 0;
   R.nxt = P.tiles[0];
+  R.nxt_idx = 0;
   if (tid == 0) ring_fill(R, 0);
   int64_t q = 0;
 

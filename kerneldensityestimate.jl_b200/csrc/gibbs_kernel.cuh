@@ -288,6 +288,7 @@ struct Ring {
   int64_t issued;  // tiles handed to the TMA unit so far (meaningful in thread 0 only)
   int ntiles;      // tiles per sample schedule
   TileDesc nxt;    // descriptor of tile `issued`, prefetched (thread 0)
+  int nxt_idx;     // issued % ntiles
 };
 
 __device__ __forceinline__ void ring_issue(const Ring &R, int64_t q, const TileDesc &td) {
@@ -304,7 +305,8 @@ __device__ __forceinline__ void ring_fill(Ring &R, int64_t consumed) {
   while (R.issued < R.known && R.issued < consumed + GB_STAGES) {
     ring_issue(R, R.issued, R.nxt);
     ++R.issued;
-    R.nxt = R.descs[(int)(R.issued % R.ntiles)];
+    if (++R.nxt_idx == R.ntiles) R.nxt_idx = 0;  // == issued % ntiles without the 64-bit division
+    R.nxt = R.descs[R.nxt_idx];
   }
 }
 
@@ -435,6 +437,7 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MINBLOCKS) gibbs_kernel(const _
   R.known = (batch < P.nbatches) ? P.ntiles : 0;
   R.issued = 0;
   R.nxt = P.tiles[0];
+  R.nxt_idx = 0;
   if (tid == 0) ring_fill(R, 0);
   int64_t q = 0;
 

@@ -52,6 +52,7 @@ def agreement(p64, i64, p32, i32):
     (1, 2, 300, 3000, 5), (2, 2, 100, 2000, 5), (3, 6, 100, 1500, 5), (4, 3, 500, 1000, 3),
     (5, 3, 200, 600, 2), (6, 2, 300, 500, 2), (7, 2, 128, 400, 1), (8, 2, 150, 400, 2),
     (2, 3, 1, 300, 3), (3, 1, 50, 300, 3), (2, 16, 20, 200, 1), (2, 2, 5001, 300, 1), (1, 3, 2, 300, 5),
+    (2, 2, 100_000, 200, 1),   # checkpoint chunks of 2048 nodes spanning several tiles, pass 2 over long chunks
 ])
 def test_same_streams_same_chains_as_fp64(d, M, N, Np, T):
     rng = np.random.default_rng(100 * d + M + N)
