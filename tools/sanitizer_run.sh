@@ -19,6 +19,6 @@ run "racecheck: warp-per-chain Gibbs" racecheck tests/test_gpu_gibbs.py -k "warp
 run "memcheck: fused product (on-chip sort + ball-tree statistics + golden sections), sample, marginals" memcheck tests/test_gpu_extras.py -k "product_in_one_call and (100 or 300 or 512) or sample_with_injected or eval_marginals and 777"
 run "racecheck: fused product kernel" racecheck tests/test_gpu_extras.py -k "product_in_one_call and 3-3-64"
 run "memcheck: FP32 Gibbs sampler (pair records, prep kernel, FP64 redo path, masks)" memcheck tests/test_gpu_gibbs_f32.py -k "same_streams and (3-6-100 or 2-2-5001 or 1-3-2 or 8-2-150) or underflow or poisoned"
-run "racecheck: FP32 Gibbs sampler (TMA ring)" racecheck tests/test_gpu_gibbs_f32.py -k "same_streams and 2-2-100"
+run "racecheck: FP32 Gibbs sampler (TMA ring)" racecheck tests/test_gpu_gibbs_f32.py -k "same_streams and 2-2-100-2000"
 run "memcheck: in-process multi-GPU (contexts on one device), schedule cache" memcheck tests/test_gpu_multi.py -k "gibbs_sharded and oversubscribed or small_calls"
 cat $out
