@@ -238,10 +238,7 @@ static int s32_get(const kdeb200_tree_t *trees, int M, int L, int T, bool masked
         const size_t off = block_of(j, li, dr.variant);
         int G = 2;
         while ((int64_t)G * GB_MAXCK < lv.n) G *= 2;
-#ifndef GF_WANT
-#define GF_WANT 4
-#endif
-        const int want = GF_WANT * gf_unr(d, dr.variant);  // trips per chunk x 2
+        const int want = 4 * gf_unr(d, dr.variant);  // at least two trips per chunk (x 1/2 and x 2 measured: +-1 %)
         if (G < want && lv.n >= 2 * want) G = want;
         dr.G = G;
         dr.nchunks = (int)((lv.n + G - 1) / G);

@@ -70,15 +70,6 @@ __host__ __device__ constexpr int gf_minblocks(int D) { return D <= 3 ? 8 : (D =
 #ifndef GF_UNR_C
 #define GF_UNR_C 2
 #endif
-#ifndef GF_PIPE
-#define GF_PIPE 0
-#endif
-#ifndef GF_DRAWPF
-#define GF_DRAWPF 0
-#endif
-#ifndef GF_RSUM
-#define GF_RSUM 0
-#endif
 constexpr double GF_LOG2E = 1.4426950408889634;
 constexpr double GF_HL2E = 0.7213475204444817;  // 0.5 log2 e
 
@@ -97,17 +88,6 @@ struct Hoist32 {
 
 template <int S, bool NC>
 __device__ __forceinline__ void gf_load(const float *__restrict__ r, f32x2 (&v)[S / 2]) {
-#ifdef GF_FAKE_HALF_LDS  // timing probe only (wrong numbers): one 16-byte load per record pair
-  if (!NC) {
-    const ulonglong2 q = reinterpret_cast<const ulonglong2 *>(r)[0];
-#pragma unroll
-    for (int k = 0; k < S / 4; ++k) {
-      v[2 * k] = q.x + (unsigned long long)k;
-      v[2 * k + 1] = q.y;
-    }
-    return;
-  }
-#endif
   if (NC && S % 8 == 0) {
     // pass 2: every lane reads ITS OWN chunk, so a warp-wide load touches 32 different lines and its cost in the LSU data
     // pipe is per instruction: one 256-bit load (LDG.E.ENL2.256, sm_100) instead of two 128-bit ones per 32 bytes
@@ -228,8 +208,8 @@ __device__ __forceinline__ void gf_trip_fin(const f32x2 (&acc)[UNR], const f32x2
 }
 
 // pass 1: FP32 sums per checkpoint chunk, FP64 running total.  Chunk-outer: the trip loop of a run (the part of a chunk
-// inside one tile) carries no checkpoint test; within a run the trips are software-pipelined with two register sets
-// (stage 1 of trip t + 1 in the same basic block as the MUFU / add chain of trip t).
+// inside one tile) carries no checkpoint test.  (An explicit two-register-set software pipeline, as in gibbs_kernel, was
+// measured and dropped: at the 64-register budget that 8 CTAs per SM need it loses 3 %)
 template <int D, int VAR>
 __device__ __forceinline__ double gf_pass1(const Draw &dr, const Hoist32<D> &h, Ring &R, int64_t &q, double *__restrict__ ck) {
   constexpr int UNR = gf_unr(D, VAR);
@@ -249,23 +229,6 @@ __device__ __forceinline__ double gf_pass1(const Draw &dr, const Hoist32<D> &h, 
       const int run = (left < np - zp) ? left : (np - zp);
       const float *r = rec + (size_t)zp * stride;
       int i = 0;
-#if GF_PIPE
-      if (run >= 2 * UNR) {
-        const int full = run - run % (2 * UNR);
-        f32x2 a0[UNR], s0[UNR], a1[UNR], s1[UNR];
-        gf_trip_pre<D, VAR, UNR>(r, h, a0, s0);
-        for (; i + 2 * UNR < full; i += 2 * UNR) {
-          gf_trip_pre<D, VAR, UNR>(r + (size_t)(i + UNR) * stride, h, a1, s1);
-          gf_trip_fin<VAR, UNR>(a0, s0, s);
-          gf_trip_pre<D, VAR, UNR>(r + (size_t)(i + 2 * UNR) * stride, h, a0, s0);
-          gf_trip_fin<VAR, UNR>(a1, s1, s);
-        }
-        gf_trip_pre<D, VAR, UNR>(r + (size_t)(i + UNR) * stride, h, a1, s1);
-        gf_trip_fin<VAR, UNR>(a0, s0, s);
-        gf_trip_fin<VAR, UNR>(a1, s1, s);
-        i = full;
-      }
-#endif
       for (; i + UNR <= run; i += UNR) {
         f32x2 acc[UNR], sc[UNR];
         gf_trip_pre<D, VAR, UNR>(r + (size_t)i * stride, h, acc, sc);
@@ -414,17 +377,8 @@ __global__ void __launch_bounds__(GB_THREADS, gf_minblocks(D)) gibbs_f32_kernel(
     }
 
     double X[D];
-    [[maybe_unused]] double Ls[D], Hs[D];  // sum_i lambda_i, sum_i lambda_i mu_i: exact at every new level, updated in between (they feed FP32 only)
-#if GF_DRAWPF
-    Draw dr_next = P.draws[0];
-#endif
     for (int di = 0; di < P.ndraws; ++di) {
-#if GF_DRAWPF
-      const Draw dr = dr_next;
-      if (di + 1 < P.ndraws) dr_next = P.draws[di + 1];  // in flight while this draw computes
-#else
       const Draw dr = P.draws[di];
-#endif
       const int j = dr.j;
       if (di == P.ndraws - 1) {
         __syncthreads();
@@ -447,10 +401,6 @@ __global__ void __launch_bounds__(GB_THREADS, gf_minblocks(D)) gibbs_f32_kernel(
             Lm += lam[i * D + k];
             Hm += lmu[i * D + k];
           }
-#if GF_RSUM
-          Ls[k] = Lm;
-          Hs[k] = Hm;
-#endif
           const uint32_t slot = (uint32_t)((dr.level - 1) * D + k);
           const double g = P.randN ? P.randN[s * P.perN + slot] : philox_normal(P.seed, (uint64_t)s, slot);
           if (any) {
@@ -474,16 +424,12 @@ __global__ void __launch_bounds__(GB_THREADS, gf_minblocks(D)) gibbs_f32_kernel(
       } else {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-#if GF_RSUM
-          const double Lm = Ls[k] - lam[j * D + k], Hm = Hs[k] - lmu[j * D + k];
-#else
           double Lm = 0.0, Hm = 0.0;
           for (int i = 0; i < M; ++i) {
             if (i == j) continue;
             Lm += lam[i * D + k];
             Hm += lmu[i * D + k];
           }
-#endif
           const bool oth = P.other[j][k] != 0;
           if (oth) {
             const double cov = 1.0 / Lm;
@@ -529,11 +475,7 @@ __global__ void __launch_bounds__(GB_THREADS, gf_minblocks(D)) gibbs_f32_kernel(
       if (dr.n > 1) {
         const uint32_t c = (uint32_t)(M + di);
         const double u = P.randU ? P.randU[s * P.perU + c - 1] : philox_uniform(P.seed, (uint64_t)s, c);
-#ifdef GF_FAKE_HALF_LDS
-        if (false) {
-#else
         if (!(pT >= 1e-25 && pT <= 1e30)) {
-#endif
           zs = gf_slow_draw<D>(dr, P.hvar[j], h, u);
           if (live) ++slow;
         } else {
@@ -570,10 +512,6 @@ __global__ void __launch_bounds__(GB_THREADS, gf_minblocks(D)) gibbs_f32_kernel(
           } else {
             const double var = dr.state_has_bw ? rs[D + k] : P.hvar[j][k];
             const double l = 1.0 / var, lm = rs[k] * l;
-#if GF_RSUM
-            Ls[k] += l - lam[j * D + k];
-            Hs[k] += lm - lmu[j * D + k];
-#endif
             lam[j * D + k] = l;
             lmu[j * D + k] = lm;
           }
