@@ -47,6 +47,26 @@ def test_error_channel_without_gpu(built):
         K.evaluateDualTree(p, np.zeros((2, 4)))
 
 
+def test_gibbs_precision_switch_is_validated(built):
+    """kdeb200_set_gibbs_precision is a process-wide host setting (no device needed): F64 / F32 accepted, the evaluation-only
+    modes rejected; the switch never reaches a CPU path -- without a GPU the sampler still fails loudly."""
+    import kde_b200 as K
+    for bad in (K.F64_BOUNDED, K.F32_BOUNDED, 7, -1):
+        with pytest.raises(K.KDEError):
+            K.set_gibbs_precision(bad)
+    K.set_gibbs_precision(K.F32)
+    K.set_gibbs_precision(K.F64)
+    import torch
+    if not torch.cuda.is_available():
+        p = K.kde(np.arange(12.0).reshape(2, 6), [1.0])
+        K.set_gibbs_precision(K.F32)
+        try:
+            with pytest.raises(K.KDEError):
+                K.prodAppxMSGibbsS(None, [p, p], None, None, Niter=1, Np=5000, seed=1)
+        finally:
+            K.set_gibbs_precision(K.F64)
+
+
 @pytest.mark.parametrize("d,N", [(1, 1), (1, 2), (1, 4), (2, 3), (3, 100), (4, 257), (2, 1024), (8, 33),
                                  (3, 70001), (1, 140000)])  # the last two take the multi-threaded path
 def test_host_tree_builder_equals_oracle(built, d, N):
