@@ -15,6 +15,7 @@ python tools/ncu_issued.py gpurun_out/ncu_issued.json "gibbs_c4:gibbs:gpurun_out
   "eval_c5:eval:gpurun_out/issued_eval.csv:eval_kernel<3:4e10:eval" "eval_c3:eval:gpurun_out/issued_eval.csv:eval_kernel<1:4e10:eval" \
   "eval_pruned_c5:eval_pruned:gpurun_out/issued_eval.csv:eval_pruned_kernel<3:4e10:eval" \
   "loo_sym_c3:eval_pruned:gpurun_out/issued_eval.csv:loo_sym_kernel<1:4e10:eval" > gpurun_out/ncu_issued.log 2>&1 || tail -5 gpurun_out/ncu_issued.log
+mkdir -p profiles; cp gpurun_out/ncu_issued.json profiles/ncu_issued.json
 KDEB200_GIBBS_WARP_MAX=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gibbs_kernel -c 1 -f -o gpurun_out/r02_gibbs python tools/prof_gibbs.py 75776 1 > /dev/null 2>&1
 python tools/ncu_summary.py gpurun_out/r02_gibbs.ncu-rep gpurun_out/r02_gibbs_ncu.txt 2>/dev/null
 timeout 400 python bench.py --impl reference > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err
